@@ -1,0 +1,196 @@
+/*
+ * probpose_b200.h - C ABI of the B200-native ProbPose inference hot path.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Every function returns 0 on
+ * success or a negative pp_status; pp_last_error() gives the message for the calling
+ * thread.  Device pointers are raw CUDA device addresses, `stream` is a cudaStream_t
+ * passed as void* (NULL = legacy default stream).  Nothing here allocates device
+ * memory: the caller sizes one workspace with pp_engine_workspace_bytes() and owns it.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference checkout, MiraPurkrabek/ProbPose_code @ 93bc991).
+ */
+#ifndef PROBPOSE_B200_H
+#define PROBPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+#define PP_MAX_KEYPOINTS 17 /* OKS sigma table length, mmpose/codecs/utils/post_processing.py:16 */
+#define PP_RECORD_FLOATS 7  /* [x_hm, y_hm, conf, prob, vis, oks, err] per keypoint */
+
+typedef enum pp_status {
+  PP_OK = 0,
+  PP_ERR_INVALID = -1,     /* bad argument (the Python layer raises ValueError)           */
+  PP_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                          */
+  PP_ERR_UNSUPPORTED = -3, /* shape or device outside what the sm_100a kernels implement   */
+  PP_ERR_STATE = -4        /* engine used before its weights were loaded, etc.             */
+} pp_status;
+
+/* GEMM arithmetic of the tensor-core path (operands staged by TMA, tcgen05.mma, fp32
+ * accumulate in TMEM).  FP16X3 is the parity mode: every operand is split into
+ * fp16 hi + scaled fp16 lo and three MMAs reproduce fp32-grade products. */
+typedef enum pp_precision {
+  PP_PREC_FP16X3 = 0, /* parity mode   (~2^-22 relative operand error)                    */
+  PP_PREC_BF16 = 1,   /* throughput mode, bf16 operands                                   */
+  PP_PREC_FP16 = 2,   /* throughput mode, fp16 operands                                   */
+  PP_PREC_FP32_SIMT = 3 /* CUDA-core fp32 FFMA GEMMs; verification of the tensor path     */
+} pp_precision;
+
+PP_API const char* pp_last_error(void);
+/* Library / build identification: "probpose_b200 <version> sm_100a". */
+PP_API const char* pp_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * Fused decode: [sparsemax(logits / T) * normalize -> clamp] x {pass, flipped pass}
+ * -> flip-TTA merge -> per-keypoint OKS-Gaussian convolution (reflect border) ->
+ * first-max argmax -> quadratic sub-pixel step -> score lookup -> record.
+ *
+ * Replaces, in one kernel launch for the whole batch:
+ *   Sparsemax + clamp        mmpose/models/heads/hybrid_heads/probmap_head.py:641-645
+ *   flip_heatmaps + average  mmpose/models/utils/tta.py:35-39, probmap_head.py:757-774
+ *   BaseHead.decode loop     mmpose/models/heads/base_head.py:57-77 (D2H copy + python loop)
+ *   ProbMap.decode           mmpose/codecs/probmap.py:170-220
+ *   get_heatmap_expected_value / _get_subpixel_maximums
+ *                            mmpose/codecs/utils/post_processing.py:308-430
+ * ---------------------------------------------------------------------------------- */
+typedef struct pp_decode_cfg {
+  int32_t num_keypoints;   /* K <= PP_MAX_KEYPOINTS                                        */
+  int32_t height, width;   /* heatmap H, W (64, 48)                                        */
+  int32_t input_is_logits; /* 1: maps are raw final-layer logits, run sparsemax here;
+                              0: maps are already-normalised heatmaps                      */
+  float temperature;       /* probmap_head.py:135 (0.5); used when input_is_logits        */
+  float normalize;         /* config `normalize` (1.0); used when input_is_logits         */
+  float error_divisor;     /* sqrt(H^2 + W^2), probmap_head.py:786-787; 0 -> computed     */
+} pp_decode_cfg;
+
+/*  maps         device (B, K, H, W) fp32
+ *  maps_flip    device (B, K, H, W) fp32 from the h-flipped input, or NULL (no TTA)
+ *  flip_indices HOST   int32[K] left/right permutation (metainfo["flip_indices"]); may be
+ *               NULL when maps_flip is NULL
+ *  scalars      device (B, 4, K) fp32 post-activation prob / vis / oks / err, or NULL
+ *  scalars_flip device (B, 4, K) fp32 from the flipped pass, or NULL
+ *  records      device (B, K, 7) fp32 out: x, y in HEATMAP pixels exactly as the
+ *               reference's `locs` (the caller applies probmap.py:218 in float64), conf =
+ *               merged heatmap at the integer peak, then prob, vis, oks, err / divisor
+ *  merged_out   device (B, K, H, W) fp32 out, or NULL: the merged normalised heatmaps
+ *               (test_cfg["output_heatmaps"], probmap_head.py:800-804)                    */
+PP_API int pp_decode(const pp_decode_cfg* cfg, const float* maps, const float* maps_flip,
+              const int32_t* flip_indices, const float* scalars, const float* scalars_flip,
+              int32_t batch, float* records, float* merged_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Tensor-core GEMM building block (exported for tests and profiling):
+ *   D[M, N] = epilogue( A[M, K] . W[N, K]^T )      A, W K-major ("TN"), fp32 accumulate
+ * Replaces the cuBLASLt / cuDNN calls behind nn.Linear / Conv2d / ConvTranspose2d on
+ * this path.
+ * ---------------------------------------------------------------------------------- */
+typedef enum pp_act { PP_ACT_NONE = 0, PP_ACT_GELU = 1, PP_ACT_RELU = 2 } pp_act;
+
+/* How the epilogue writes a result row m / column n. */
+typedef enum pp_out_kind {
+  PP_OUT_F32 = 0,      /* fp32 (M, ldd) row-major                                          */
+  PP_OUT_OPERAND = 1,  /* next GEMM's A operand in the engine precision (see pp_operand_*) */
+  PP_OUT_PLANES = 2    /* fp32 (M / plane, N, plane): channel-major planes (final 1x1 conv
+                          -> (B, K, H*W) logits)                                           */
+} pp_out_kind;
+
+typedef struct pp_gemm_args {
+  int32_t precision;      /* pp_precision                                                  */
+  int32_t m, n, k;        /* logical sizes; k % 64 == 0, n % 8 == 0                        */
+  const void* a;          /* device operand (see pp_operand_bytes)                         */
+  const void* w;          /* device operand, N rows                                        */
+  const float* scale;     /* device fp32[n] or NULL (=1): per-column multiplier (BN fold)  */
+  const float* shift;     /* device fp32[n] or NULL (=0): per-column bias                  */
+  const float* residual;  /* device fp32 (M, ldd) or NULL: added after activation          */
+  int32_t act;            /* pp_act                                                        */
+  int32_t out_kind;       /* pp_out_kind                                                   */
+  void* d;                /* device output                                                 */
+  int32_t ldd;            /* PP_OUT_F32: leading dim (floats); PP_OUT_OPERAND: logical K of
+                             the produced operand; PP_OUT_PLANES: ignored                  */
+  int32_t plane;          /* PP_OUT_PLANES: rows per plane (H*W)                           */
+  /* optional row scatter for the 4 sub-pixel phases of ConvTranspose2d(k4,s2,p1):
+   * logical row m = (b*hin + i)*win + j is written to ((b*2hin + 2i+py)*2win + 2j+px).    */
+  int32_t up_hin, up_win, up_py, up_px; /* up_hin == 0 disables                            */
+  int32_t tile_n;         /* 0 = auto; else 32/64/128/192/256 output-tile width (tuning)   */
+} pp_gemm_args;
+
+PP_API int pp_gemm(const pp_gemm_args* args, void* stream);
+
+/* Bytes of an (rows x k) GEMM operand in `precision`, and the converter from fp32
+ * row-major (device -> device) used for weights and by tests. */
+PP_API size_t pp_operand_bytes(int32_t precision, int64_t rows, int64_t k);
+PP_API int pp_operand_from_f32(int32_t precision, const float* src, int64_t rows, int64_t k, int64_t ld_src,
+                        void* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Engine: the whole forward (preprocess -> ViT -> ProbMapHead -> fused decode).
+ * Replaces TopdownPoseEstimator.predict (mmpose/models/pose_estimators/topdown.py:86-126)
+ * = PoseDataPreprocessor.forward (models/data_preprocessors/data_preprocessor.py:79-104)
+ * + mmpretrain VisionTransformer.forward (config :56-67) + ProbMapHead.predict
+ * (probmap_head.py:715-804).
+ * ---------------------------------------------------------------------------------- */
+typedef struct pp_engine_cfg {
+  int32_t precision;        /* pp_precision                                                */
+  int32_t max_batch;        /* crops per call, BEFORE flip doubling                        */
+  int32_t img_h, img_w;     /* 256, 192                                                    */
+  int32_t patch, patch_pad; /* 16, 2                                                       */
+  int32_t embed_dim, depth, heads, ffn_dim; /* 384, 12, 12, 1536 (ViT-S) / 768,12,12,3072  */
+  int32_t num_keypoints;    /* 17                                                          */
+  int32_t deconv_channels;  /* 256 (two deconv layers); 0 = backbone-only engine           */
+  float ln_eps;             /* 1e-6                                                        */
+  float bn_eps;             /* 1e-5                                                        */
+  float temperature, normalize; /* 0.5, 1.0                                                */
+  float mean[3], std[3];    /* RGB order, applied after BGR->RGB                           */
+} pp_engine_cfg;
+
+typedef struct pp_engine pp_engine;
+
+PP_API size_t pp_engine_workspace_bytes(const pp_engine_cfg* cfg);
+/* `workspace` is device memory of at least pp_engine_workspace_bytes(cfg), 1024-byte
+ * aligned, owned by the caller and alive until pp_engine_destroy. */
+PP_API int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_t workspace_bytes, pp_engine** out);
+PP_API void pp_engine_destroy(pp_engine* e);
+
+/* Load one tensor by its MMPose state_dict name ("backbone.layers.3.attn.qkv.weight",
+ * "head.deconv_layers.0.weight", ...) from fp32 device memory of
+ * `numel` elements.  Unknown names return PP_ERR_INVALID.  Call pp_engine_finalize once
+ * all tensors are in; it folds BatchNorm and checks nothing is missing. */
+PP_API int pp_engine_load(pp_engine* e, const char* name, const float* data, int64_t numel, void* stream);
+PP_API int pp_engine_finalize(pp_engine* e, void* stream);
+
+/* Backbone only: x fp32 (B, 3, H, W) normalised RGB -> feat fp32 (B, C, h, w) NCHW,
+ * exactly VisionTransformer.forward's featmap (out_type="featmap"). */
+PP_API int pp_engine_backbone(pp_engine* e, const float* x, int32_t batch, float* feat_nchw, void* stream);
+
+/* Head forward on NCHW features (ProbMapHead.forward, probmap_head.py:600-625):
+ * heat_logits fp32 (B, K, 4h, 4w) raw final-layer output (sparsemax is fused into
+ * pp_decode); scalars fp32 (B, 4, K) post-activation prob / vis / oks / err. */
+PP_API int pp_engine_head(pp_engine* e, const float* feat_nchw, int32_t batch, float* heat_logits,
+                   float* scalars, void* stream);
+
+/* End to end.  Exactly one of crops_u8_bgr (B,3,H,W uint8 BGR, preprocessing fused) and
+ * x_f32 (B,3,H,W fp32 already normalised RGB) is non-NULL.  flip_test != 0 runs the
+ * mirrored pass too and merges as the reference does.  records: (B, K, 7) fp32 as in
+ * pp_decode.  merged_out may be NULL. */
+PP_API int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const float* x_f32, int32_t batch,
+                    int32_t flip_test, const int32_t* flip_indices, float* records, float* merged_out,
+                    void* stream);
+
+/* Number of kernels the last pp_engine_* call launched (bench.py's gpu_launches). */
+PP_API int64_t pp_engine_last_launch_count(const pp_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBPOSE_B200_H */

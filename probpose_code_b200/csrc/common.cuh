@@ -1,0 +1,135 @@
+// Shared helpers for the probpose_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/probpose_b200.h"
+
+namespace pp {
+
+// ---- error plumbing ------------------------------------------------------------------
+void set_error(const char* fmt, ...);  // defined in capi.cu (thread-local buffer)
+
+#define PP_CHECK_CUDA(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      pp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return PP_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define PP_REQUIRE(cond, status, ...)                                                     \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      pp::set_error(__VA_ARGS__);                                                         \
+      return (status);                                                                    \
+    }                                                                                     \
+  } while (0)
+
+// Launch counter (bench.py's gpu_launches); bumped by every host-side launcher.
+extern thread_local int64_t g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Streaming 128-bit load that does not pollute L1 (data is touched once).
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---- GEMM operand formats --------------------------------------------------------------
+// An "operand" is the K-major matrix a tensor-core GEMM reads through TMA.
+//   FP16X3 : fp16 (rows, 2K): [hi | lo * 2^11], hi = rn16(a), lo = rn16((a - hi) * 2048)
+//   BF16   : bf16 (rows, K)
+//   FP16   : fp16 (rows, K)
+//   FP32   : fp32 (rows, K)   (CUDA-core verification path)
+constexpr float kLoScale = 2048.0f;
+constexpr float kLoScaleInv = 1.0f / 2048.0f;
+
+__host__ __device__ inline int operand_elem_bytes(int prec) { return prec == PP_PREC_FP32_SIMT ? 4 : 2; }
+__host__ __device__ inline int64_t operand_row_elems(int prec, int64_t k) { return prec == PP_PREC_FP16X3 ? 2 * k : k; }
+
+__device__ __forceinline__ __half sat_half(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+}
+
+// Write logical element (row, col) = v of an operand with logical width k.
+template <int PREC>
+__device__ __forceinline__ void store_operand(void* base, int64_t row, int col, int k, float v) {
+  if constexpr (PREC == PP_PREC_FP16X3) {
+    __half* p = reinterpret_cast<__half*>(base) + row * (2 * (int64_t)k);
+    __half hi = sat_half(v);
+    p[col] = hi;
+    p[k + col] = sat_half((v - __half2float(hi)) * kLoScale);
+  } else if constexpr (PREC == PP_PREC_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(base)[row * (int64_t)k + col] = __float2bfloat16_rn(v);
+  } else if constexpr (PREC == PP_PREC_FP16) {
+    reinterpret_cast<__half*>(base)[row * (int64_t)k + col] = sat_half(v);
+  } else {
+    reinterpret_cast<float*>(base)[row * (int64_t)k + col] = v;
+  }
+}
+
+// Vector form: 4 consecutive columns (col % 4 == 0).
+template <int PREC>
+__device__ __forceinline__ void store_operand4(void* base, int64_t row, int col, int k, float4 v) {
+  if constexpr (PREC == PP_PREC_FP16X3) {
+    __half* p = reinterpret_cast<__half*>(base) + row * (2 * (int64_t)k);
+    __half h0 = sat_half(v.x), h1 = sat_half(v.y), h2 = sat_half(v.z), h3 = sat_half(v.w);
+    __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
+    __half2 c = __halves2half2(sat_half((v.x - __half2float(h0)) * kLoScale), sat_half((v.y - __half2float(h1)) * kLoScale));
+    __half2 d = __halves2half2(sat_half((v.z - __half2float(h2)) * kLoScale), sat_half((v.w - __half2float(h3)) * kLoScale));
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<uint32_t*>(&a); hi.y = *reinterpret_cast<uint32_t*>(&b);
+    lo.x = *reinterpret_cast<uint32_t*>(&c); lo.y = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint2*>(p + col) = hi;
+    *reinterpret_cast<uint2*>(p + k + col) = lo;
+  } else if constexpr (PREC == PP_PREC_BF16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + row * (int64_t)k + col) = o;
+  } else if constexpr (PREC == PP_PREC_FP16) {
+    __half2 a = __halves2half2(sat_half(v.x), sat_half(v.y)), b = __halves2half2(sat_half(v.z), sat_half(v.w));
+    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + row * (int64_t)k + col) = o;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + row * (int64_t)k + col) = v;
+  }
+}
+
+// Dispatch a templated-on-precision callable.
+#define PP_DISPATCH_PREC(prec, ...)                                   \
+  switch (prec) {                                                     \
+    case PP_PREC_FP16X3: { constexpr int PREC = PP_PREC_FP16X3; __VA_ARGS__; break; }       \
+    case PP_PREC_BF16: { constexpr int PREC = PP_PREC_BF16; __VA_ARGS__; break; }           \
+    case PP_PREC_FP16: { constexpr int PREC = PP_PREC_FP16; __VA_ARGS__; break; }           \
+    default: { constexpr int PREC = PP_PREC_FP32_SIMT; __VA_ARGS__; break; }                \
+  }
+
+}  // namespace pp

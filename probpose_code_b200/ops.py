@@ -1,0 +1,113 @@
+"""Thin Python wrappers over the C ABI: torch tensors in/out only at this boundary
+(``data_ptr()`` + shape + current CUDA stream).  No fallback paths."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise _lib.PPError(f"{name} must live on a CUDA device: probpose_code_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def decode(maps: torch.Tensor, maps_flip: Optional[torch.Tensor] = None,
+           flip_indices: Optional[Sequence[int]] = None, scalars: Optional[torch.Tensor] = None,
+           scalars_flip: Optional[torch.Tensor] = None, *, input_is_logits: bool, temperature: float = 0.5,
+           normalize: float = 1.0, return_heatmaps: bool = False, out: Optional[torch.Tensor] = None):
+    """Fused decode (``pp_decode``).  ``maps`` (B, K, H, W) fp32 CUDA.  Returns records
+    (B, K, 7) fp32 [x_hm, y_hm, conf, prob, vis, oks, err/diag] and, optionally, the merged
+    normalised heatmaps (B, K, H, W)."""
+    _need_cuda(maps, "maps")
+    if maps.dim() != 4:
+        raise ValueError(f"maps must be (B, K, H, W), got {tuple(maps.shape)}")
+    b, k, h, w = maps.shape
+    for name, t in (("maps_flip", maps_flip),):
+        if t is not None:
+            _need_cuda(t, name)
+            if t.shape != maps.shape:
+                raise ValueError(f"{name} shape {tuple(t.shape)} != maps shape {tuple(maps.shape)}")
+    for name, t in (("scalars", scalars), ("scalars_flip", scalars_flip)):
+        if t is not None:
+            _need_cuda(t, name)
+            if tuple(t.shape) != (b, 4, k):
+                raise ValueError(f"{name} must be (B, 4, K) = {(b, 4, k)}, got {tuple(t.shape)}")
+    fi = None
+    if maps_flip is not None:
+        if flip_indices is None:
+            raise ValueError("flip_indices are required with maps_flip")
+        assert len(flip_indices) == k, "flip_indices length must equal the number of keypoints"
+        fi = (C.c_int32 * k)(*[int(i) for i in flip_indices])
+    cfg = _lib.DecodeCfg(k, h, w, int(input_is_logits), float(temperature), float(normalize),
+                         float(math.sqrt(h * h + w * w)))
+    rec = out if out is not None else torch.empty((b, k, _lib.RECORD_FLOATS), dtype=torch.float32, device=maps.device)
+    if out is not None:
+        _need_cuda(out, "out")
+        if tuple(out.shape) != (b, k, _lib.RECORD_FLOATS):
+            raise ValueError("out must be (B, K, 7)")
+    merged = torch.empty_like(maps) if return_heatmaps else None
+    with torch.cuda.device(maps.device):
+        check(lib().pp_decode(C.byref(cfg), _ptr(maps), _ptr(maps_flip), fi, _ptr(scalars), _ptr(scalars_flip),
+                              b, _ptr(rec), _ptr(merged), _stream()), "pp_decode")
+    return (rec, merged) if return_heatmaps else rec
+
+
+def to_operand(x: torch.Tensor, precision: int) -> torch.Tensor:
+    """fp32 (rows, k) CUDA -> GEMM operand buffer (uint8 tensor) in ``precision``."""
+    _need_cuda(x, "x")
+    rows, k = x.shape
+    buf = torch.empty(lib().pp_operand_bytes(precision, rows, k), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().pp_operand_from_f32(precision, x.data_ptr(), rows, k, k, buf.data_ptr(), _stream()),
+              "pp_operand_from_f32")
+    return buf
+
+
+def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precision: int, *,
+         scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE, out_kind: int = _lib.OUT_F32,
+         out: Optional[torch.Tensor] = None, ldd: Optional[int] = None, plane: int = 0, up=None, tile_n: int = 0):
+    """``pp_gemm``: D = epilogue(A . W^T).  ``a_op`` / ``w_op`` are operand buffers from
+    :func:`to_operand`.  Returns the output tensor (fp32, or a uint8 operand buffer)."""
+    dev = a_op.device
+    if out_kind == _lib.OUT_F32:
+        ldd = n if ldd is None else ldd
+        rows = m if up is None else m * 4
+        if out is None:
+            out = torch.empty((rows, ldd), dtype=torch.float32, device=dev)
+    elif out_kind == _lib.OUT_OPERAND:
+        ldd = n if ldd is None else ldd
+        rows = m if up is None else m * 4
+        if out is None:
+            out = torch.zeros(lib().pp_operand_bytes(precision, rows, ldd), dtype=torch.uint8, device=dev)
+    else:
+        assert plane > 0 and m % plane == 0
+        ldd = 0
+        if out is None:
+            out = torch.empty((m // plane, n, plane), dtype=torch.float32, device=dev)
+    hin, win, py, px = up if up is not None else (0, 0, 0, 0)
+    args = _lib.GemmArgs(precision, m, n, k, a_op.data_ptr(), w_op.data_ptr(), _ptr(scale), _ptr(shift),
+                         _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n)
+    with torch.cuda.device(dev):
+        check(lib().pp_gemm(C.byref(args), _stream()), "pp_gemm")
+    return out

@@ -1,0 +1,147 @@
+"""Parity of the fused CUDA decode kernel (through the C ABI) with the oracle and with the
+golden vectors captured from the genuine reference code."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle import decode_oracle as d
+
+pytestmark = pytest.mark.gpu
+
+# identical heatmap bits in -> locations within this many heatmap pixels (1e-3 input px ~ 2.4e-4 hm px)
+LOC_TOL = 2e-4
+
+
+def _ops():
+    from probpose_code_b200 import ops
+    return ops
+
+
+def _cmp(rec, locs, vals, tol=LOC_TOL):
+    rec = rec.cpu().numpy()
+    dl = np.abs(rec[..., :2] - locs)
+    assert dl.max() <= tol, f"max |dloc| {dl.max()} at {np.unravel_index(dl.argmax(), dl.shape)}"
+    np.testing.assert_array_equal(rec[..., 2], vals)
+
+
+FAMILIES = {
+    "planted": lambda: d.heatmaps_from_logits(cases.planted_peak_logits(12, seed=0)),
+    "noise_1e-3": lambda: d.heatmaps_from_logits(cases.noise_logits(3, 1, 1e-3)),
+    "noise_1e-1": lambda: d.heatmaps_from_logits(cases.noise_logits(3, 2, 1e-1)),
+    "noise_1": lambda: d.heatmaps_from_logits(cases.noise_logits(3, 3, 1.0)),
+    "uniform": lambda: cases.uniform_heatmaps(3, 4),
+    "special": cases.special_heatmaps,
+}
+
+
+@pytest.mark.parametrize("name", list(FAMILIES))
+def test_heatmap_input_against_reference_golden(golden, name):
+    hms = FAMILIES[name]()
+    rec = _ops().decode(torch.from_numpy(hms).cuda(), input_is_logits=False)
+    _cmp(rec, golden[f"{name}/locs"], golden[f"{name}/vals"])
+    assert (rec[..., 3:].cpu().numpy() == 0).all()  # no scalars given
+
+
+@pytest.mark.parametrize("gen,kw", [
+    (cases.planted_peak_logits, dict(batch=32, seed=11)),
+    (cases.noise_logits, dict(batch=4, seed=12, std=1e-3)),
+    (cases.noise_logits, dict(batch=4, seed=13, std=0.2)),
+    (cases.noise_logits, dict(batch=4, seed=14, std=3.0)),
+])
+def test_logit_input_fused_sparsemax(gen, kw):
+    z = gen(**kw)
+    hm = d.heatmaps_from_logits(z)
+    locs, vals = d.expected_value_decode_batch(hm)
+    rec, merged = _ops().decode(torch.from_numpy(z).cuda(), input_is_logits=True, return_heatmaps=True)
+    merged = merged.cpu().numpy()
+    # sparsemax itself: same support up to boundary elements, values within fp32 summation noise
+    np.testing.assert_allclose(merged, hm, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(merged.reshape(*merged.shape[:2], -1).sum(-1), 1.0, atol=1e-4)
+    r = rec.cpu().numpy()
+    # decode of the kernel's own heatmaps (identical bits) must match the oracle tightly ...
+    locs_k, vals_k = d.expected_value_decode_batch(merged)
+    assert np.abs(r[..., :2] - locs_k).max() <= LOC_TOL
+    np.testing.assert_array_equal(r[..., 2], vals_k)
+    # ... and end to end vs. the oracle's sparsemax within the 1e-3 input-px budget
+    assert np.abs(r[..., :2] - locs).max() <= 2.4e-4
+    np.testing.assert_allclose(r[..., 2], vals, atol=2e-6)
+
+
+def test_flip_tta_merge_and_scalars():
+    fi = d.COCO_FLIP_INDICES
+    z = cases.planted_peak_logits(16, seed=21)
+    zf = cases.planted_peak_logits(16, seed=22)
+    rng = np.random.default_rng(5)
+    s, sf = rng.random((16, 4, 17), dtype=np.float32), rng.random((16, 4, 17), dtype=np.float32)
+    merged_o = d.tta_merge(d.heatmaps_from_logits(z), d.heatmaps_from_logits(zf), fi)
+    locs, vals = d.expected_value_decode_batch(merged_o)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    rec, merged = _ops().decode(cu(z), cu(zf), fi, cu(s), cu(sf), input_is_logits=True, return_heatmaps=True)
+    np.testing.assert_allclose(merged.cpu().numpy(), merged_o, rtol=0, atol=2e-6)
+    r = rec.cpu().numpy()
+    assert np.abs(r[..., :2] - locs).max() <= 2.4e-4
+    np.testing.assert_allclose(r[..., 2], vals, atol=2e-6)
+    sm = (s + sf[:, :, fi]) * np.float32(0.5)
+    np.testing.assert_array_equal(r[..., 3], sm[:, 0])
+    np.testing.assert_array_equal(r[..., 4], sm[:, 1])
+    np.testing.assert_array_equal(r[..., 5], sm[:, 2])
+    np.testing.assert_allclose(r[..., 6], sm[:, 3] / np.float32(80.0), rtol=1e-6)
+    # heatmap-input TTA (already normalised maps) and scalars without a flipped set
+    p, pf = d.heatmaps_from_logits(z), d.heatmaps_from_logits(zf)
+    rec2 = _ops().decode(cu(p), cu(pf), fi, cu(s), None, input_is_logits=False).cpu().numpy()
+    assert np.abs(rec2[..., :2] - locs).max() <= LOC_TOL
+    np.testing.assert_array_equal(rec2[..., 3], s[:, 0])
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 3 size (batch 256): size-independent properties instead of the slow oracle."""
+    z = cases.planted_peak_logits(256, seed=3)
+    zc = torch.from_numpy(z).cuda()
+    rec, merged = _ops().decode(zc, input_is_logits=True, return_heatmaps=True)
+    r, m = rec.cpu().numpy(), merged.cpu().numpy()
+    assert np.isfinite(r).all()
+    assert (r[..., 0] >= 0).all() and (r[..., 0] <= 47).all() and (r[..., 1] >= 0).all() and (r[..., 1] <= 63).all()
+    np.testing.assert_allclose(m.reshape(256, 17, -1).sum(-1), 1.0, atol=1e-4)
+    # idempotence: decoding the kernel's own heatmaps gives the same records
+    r2 = _ops().decode(merged, input_is_logits=False).cpu().numpy()
+    np.testing.assert_array_equal(r2[..., :3], r[..., :3])
+    # batch independence: a permuted batch gives permuted records
+    perm = torch.randperm(256, generator=torch.Generator().manual_seed(0))
+    r3 = _ops().decode(zc[perm.cuda()].contiguous(), input_is_logits=True).cpu().numpy()
+    np.testing.assert_array_equal(r3, r[perm.numpy()])
+    # mirror symmetry: TTA of a map with its own mirror image is symmetric -> x within [0, 47] and
+    # the un-flipped channel decode of (z, mirror(z)[flip]) equals decode of the symmetrised map
+    fi = d.COCO_FLIP_INDICES
+    inv = np.argsort(fi)
+    zf = torch.from_numpy(np.ascontiguousarray(z[:, inv][..., ::-1])).cuda()
+    rs, ms = _ops().decode(zc, zf, fi, input_is_logits=True, return_heatmaps=True)
+    np.testing.assert_allclose(ms.cpu().numpy(), m, atol=1e-6)  # 0.5 * (P + P) == P
+
+
+def test_empty_and_ragged_batches():
+    ops = _ops()
+    rec = ops.decode(torch.empty((0, 17, 64, 48), device="cuda"), input_is_logits=True)
+    assert rec.shape == (0, 17, 7)
+    for b in (1, 3, 7):
+        z = cases.planted_peak_logits(b, seed=b)
+        locs, vals = d.expected_value_decode_batch(d.heatmaps_from_logits(z))
+        r = ops.decode(torch.from_numpy(z).cuda(), input_is_logits=True).cpu().numpy()
+        assert np.abs(r[..., :2] - locs).max() <= 2.4e-4
+    # fewer keypoints than 17 uses the first K sigmas (post_processing.py:19-21)
+    hm = cases.uniform_heatmaps(2, 9)[:, :5].copy()
+    locs, vals = d.expected_value_decode_batch(hm)
+    r = ops.decode(torch.from_numpy(hm).cuda(), input_is_logits=False).cpu().numpy()
+    assert np.abs(r[..., :2] - locs).max() <= LOC_TOL
+
+
+def test_negative_and_arbitrary_heatmaps():
+    """decode() is a public codec API and may be handed anything, not only sparsemax output."""
+    rng = np.random.default_rng(8)
+    hm = rng.normal(0, 1, (3, 17, 64, 48)).astype(np.float32)
+    locs, vals = d.expected_value_decode_batch(hm)
+    r = _ops().decode(torch.from_numpy(hm).cuda(), input_is_logits=False).cpu().numpy()
+    assert np.abs(r[..., :2] - locs).max() <= 5e-4
+    np.testing.assert_array_equal(r[..., 2], vals)

@@ -1,0 +1,111 @@
+"""The tcgen05 GEMM (through pp_gemm) against an fp64 torch matmul, all precisions / epilogues."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from probpose_code_b200 import _lib  # noqa: E402
+
+TOL = {_lib.PREC_FP16X3: 3e-6, _lib.PREC_BF16: 1.2e-2, _lib.PREC_FP16: 1.5e-3, _lib.PREC_FP32_SIMT: 2e-6}
+
+
+def _ops():
+    from probpose_code_b200 import ops
+    return ops
+
+
+def _operand_to_f64(buf, rows, k, prec):
+    """Decode an operand buffer back to float64 (what the tensor cores will multiply)."""
+    if prec == _lib.PREC_FP32_SIMT:
+        return buf.view(torch.float32).view(rows, k).double()
+    if prec == _lib.PREC_BF16:
+        return buf.view(torch.bfloat16).view(rows, k).double()
+    if prec == _lib.PREC_FP16:
+        return buf.view(torch.float16).view(rows, k).double()
+    h = buf.view(torch.float16).view(rows, 2 * k).double()
+    return h[:, :k] + h[:, k:] / 2048.0
+
+
+def _rel(a, ref):
+    return ((a.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_BF16, _lib.PREC_FP16, _lib.PREC_FP32_SIMT])
+@pytest.mark.parametrize("m,n,k", [(256, 384, 384), (192, 1152, 384), (1000, 1536, 384), (640, 384, 1536),
+                                   (128, 256, 1024), (300, 64, 128), (77, 17, 256)])
+def test_plain_gemm(prec, m, n, k):
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) * 0.05
+    ops = _ops()
+    ao, wo = ops.to_operand(a, prec), ops.to_operand(w, prec)
+    # operand round trip is itself part of the contract
+    assert _rel(_operand_to_f64(ao, m, k, prec), a.double()) <= {0: 3e-7, 1: 4e-3, 2: 5e-4, 3: 0}[prec]
+    out = ops.gemm(ao, wo, m, n, k, prec)
+    ref = a.double() @ w.double().t()
+    assert _rel(out, ref) <= TOL[prec], f"rel err {_rel(out, ref)}"
+    if prec != _lib.PREC_FP32_SIMT:  # against exactly what the tensor cores were given: accumulation error only
+        ref_q = _operand_to_f64(ao, m, k, prec) @ _operand_to_f64(wo, n, k, prec).t()
+        assert _rel(out, ref_q) <= 3e-6
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_BF16, _lib.PREC_FP32_SIMT])
+@pytest.mark.parametrize("tile_n", [0, 32, 64, 128, 192, 256])
+def test_tile_widths(prec, tile_n):
+    if prec == _lib.PREC_FP32_SIMT and tile_n:
+        pytest.skip("tile_n only applies to the tensor-core kernel")
+    m, n, k = 384, 768, 512
+    g = torch.Generator(device="cuda").manual_seed(tile_n)
+    a, w = torch.randn(m, k, device="cuda", generator=g), torch.randn(n, k, device="cuda", generator=g) * 0.05
+    ops = _ops()
+    out = ops.gemm(ops.to_operand(a, prec), ops.to_operand(w, prec), m, n, k, prec, tile_n=tile_n)
+    assert _rel(out, a.double() @ w.double().t()) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_BF16, _lib.PREC_FP32_SIMT])
+def test_epilogues(prec):
+    ops = _ops()
+    m, n, k = 384, 384, 384
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a, w = torch.randn(m, k, device="cuda", generator=g), torch.randn(n, k, device="cuda", generator=g) * 0.05
+    scale, shift = torch.rand(n, device="cuda", generator=g) + 0.5, torch.randn(n, device="cuda", generator=g)
+    res = torch.randn(m, n, device="cuda", generator=g)
+    ao, wo = ops.to_operand(a, prec), ops.to_operand(w, prec)
+    acc = a.double() @ w.double().t()
+    tol = TOL[prec] * 4
+    # bias + GELU
+    out = ops.gemm(ao, wo, m, n, k, prec, shift=shift, act=_lib.ACT_GELU)
+    assert _rel(out, torch.nn.functional.gelu(acc + shift.double())) <= tol
+    # BN-style scale/shift + ReLU
+    out = ops.gemm(ao, wo, m, n, k, prec, scale=scale, shift=shift, act=_lib.ACT_RELU)
+    assert _rel(out, torch.relu(acc * scale.double() + shift.double())) <= tol
+    # bias + residual (in place on the residual stream, like x += proj(...))
+    out = ops.gemm(ao, wo, m, n, k, prec, shift=shift, residual=res, out=res.clone())
+    assert _rel(out, acc + shift.double() + res.double()) <= tol
+    # operand output feeds the next GEMM
+    nxt = ops.gemm(ao, wo, m, n, k, prec, shift=shift, act=_lib.ACT_GELU, out_kind=_lib.OUT_OPERAND)
+    back = _operand_to_f64(nxt, m, n, prec)
+    assert _rel(back, torch.nn.functional.gelu(acc + shift.double())) <= max(tol, {0: 3e-6, 1: 8e-3, 3: 2e-6}[prec])
+    # channel-major planes, N = 17 (final 1x1 conv)
+    w17 = w[:17].contiguous()
+    out = ops.gemm(ao, ops.to_operand(w17, prec), m, 17, k, prec, shift=shift[:17].contiguous(), out_kind=_lib.OUT_PLANES, plane=96)
+    ref = (acc[:, :17] + shift[:17].double()).view(4, 96, 17).permute(0, 2, 1)
+    assert out.shape == (4, 17, 96) and _rel(out, ref) <= tol
+    # deconv phase scatter: rows (b, i, j) -> (b, 2i+py, 2j+px)
+    hin, win = 8, 12  # m = 4 * 96
+    full = torch.zeros(4 * m, n, device="cuda")
+    for py in range(2):
+        for px in range(2):
+            ops.gemm(ao, wo, m, n, k, prec, out=full, up=(hin, win, py, px))
+    v = full.view(4, 2 * hin, 2 * win, n)
+    for py in range(2):
+        for px in range(2):
+            assert _rel(v[:, py::2, px::2].reshape(m, n), acc) <= tol
+
+
+def test_argument_validation_needs_no_launch():
+    ops = _ops()
+    a = torch.zeros(128, 100, device="cuda")
+    with pytest.raises(ValueError):
+        ops.gemm(ops.to_operand(a, _lib.PREC_BF16), ops.to_operand(a, _lib.PREC_BF16), 128, 128, 100, _lib.PREC_BF16)
