@@ -329,8 +329,9 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
                          const int32_t* flip_indices, const float* scalars, const float* scalars_flip,
                          int32_t batch, float* records, float* merged_out, void* stream) {
   using namespace pp;
-  PP_REQUIRE(cfg && maps && records, PP_ERR_INVALID, "pp_decode: cfg, maps and records must be non-NULL");
+  PP_REQUIRE(cfg != nullptr, PP_ERR_INVALID, "pp_decode: cfg must be non-NULL");
   PP_REQUIRE(batch >= 0, PP_ERR_INVALID, "pp_decode: negative batch %d", batch);
+  PP_REQUIRE(batch == 0 || (maps && records), PP_ERR_INVALID, "pp_decode: maps and records must be non-NULL");
   PP_REQUIRE(cfg->num_keypoints >= 1 && cfg->num_keypoints <= PP_MAX_KEYPOINTS, PP_ERR_INVALID,
              "pp_decode: num_keypoints %d outside [1, %d] (OKS sigma table, post_processing.py:16)",
              cfg->num_keypoints, PP_MAX_KEYPOINTS);
