@@ -123,6 +123,8 @@ typedef struct pp_gemm_args {
    * logical row m = (b*hin + i)*win + j is written to ((b*2hin + 2i+py)*2win + 2j+px).    */
   int32_t up_hin, up_win, up_py, up_px; /* up_hin == 0 disables                            */
   int32_t tile_n;         /* 0 = auto; else 32/64/128/192/256 output-tile width (tuning)   */
+  int32_t res_mod;        /* > 0: the residual has res_mod rows and output row r adds row
+                             r % res_mod (pos_embed broadcast over the batch); 0 = (M, ldd)  */
 } pp_gemm_args;
 
 PP_API int pp_gemm(const pp_gemm_args* args, void* stream);

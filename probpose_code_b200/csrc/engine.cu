@@ -1,0 +1,533 @@
+// pp_engine: the whole ProbPose forward on one GPU, as a fixed sequence of kernel launches on
+// the caller's stream inside one caller-owned workspace (no allocation, no host sync).
+//
+//   crops (uint8 BGR or normalised fp32) --patchify (+ mirrored pass)--> patch GEMM + pos_embed
+//   -> depth x [LN -> qkv GEMM -> attention -> proj GEMM (+x) -> LN -> fc1 GEMM + GELU -> fc2 GEMM (+x)]
+//   -> LN -> features (B, gh, gw, D) as a GEMM operand
+//   -> heatmap branch: 2 x [4 sub-pixel phase GEMMs of ConvTranspose2d(k4,s2,p1) + BN + ReLU] -> 1x1 conv -> logits
+//   -> 4 scalar branches: merged 3x3 conv GEMM + BN -> MaxPool -> ReLU -> ... -> 1x1 conv -> sigmoid / ReLU
+//   -> fused decode (decode.cu): sparsemax, flip-TTA merge, OKS convolution, argmax, sub-pixel, record.
+//
+// Reference call chain replaced: TopdownPoseEstimator.predict (topdown.py:86-126) -> extract_feat
+// (base.py:196-210) -> ProbMapHead.predict (probmap_head.py:715-804) -> BaseHead.decode
+// (base_head.py:33-86) -> ProbMap.decode (probmap.py:170-220).
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "engine_ops.cuh"
+
+namespace pp {
+
+namespace {
+
+struct Param {
+  std::string name;
+  int64_t numel;
+  size_t off;  // bytes from the workspace base
+  int group;   // 0 backbone, 1 head
+  bool loaded;
+};
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 1023) & ~size_t(1023);
+    return o;
+  }
+};
+
+const char* kBranches[4] = {"probability", "visibility", "oks", "error"};
+
+}  // namespace
+
+}  // namespace pp
+
+struct pp_engine {
+  pp_engine_cfg cfg;
+  int prec;
+  int gh, gw, tokens, D, FF, heads, dh, depth, K, DC, PK;  // PK = 3 * patch^2
+  int max_b2;                                              // 2 * max_batch (flip doubling)
+  uint8_t* base;
+  size_t bytes;
+  std::vector<pp::Param> params;
+  std::unordered_map<std::string, int> index;
+  bool backbone_ready = false, head_ready = false;
+  int64_t last_launches = 0;
+
+  // packed weights (byte offsets)
+  size_t w_patch;
+  struct Layer { size_t wqkv, wproj, wfc1, wfc2; };
+  std::vector<Layer> layers;
+  size_t w_dc[2][4], dc_scale[2], dc_shift[2], w_final;
+  size_t w_c1, w_c2[4], w_c3[4], c_scale[3], c_shift[3], tail_w, tail_b;
+  // activations (byte offsets)
+  size_t x, a_op, qkv, h_op, feat_op, feat_f32;
+  size_t g_op, d1_op, d2_op, logits, c_f32, pool_op, scal, pack_tmp;
+
+  template <typename T = void>
+  T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
+  const float* P(const std::string& name) const { return at<float>(params[index.at(name)].off); }
+};
+
+namespace pp {
+
+static void add_param(pp_engine* e, Bump& bump, const std::string& name, int64_t numel, int group) {
+  Param p;
+  p.name = name; p.numel = numel; p.group = group; p.loaded = false;
+  p.off = bump.take((size_t)numel * sizeof(float));
+  e->index[name] = (int)e->params.size();
+  e->params.push_back(p);
+}
+
+// Lays out parameters, packed weights and activations.  Used both to size the workspace
+// (pp_engine_workspace_bytes) and to fill the engine's offsets (pp_engine_create).
+static size_t plan(pp_engine* e) {
+  const pp_engine_cfg& c = e->cfg;
+  e->prec = c.precision;
+  e->gh = (c.img_h + 2 * c.patch_pad - c.patch) / c.patch + 1;
+  e->gw = (c.img_w + 2 * c.patch_pad - c.patch) / c.patch + 1;
+  e->tokens = e->gh * e->gw;
+  e->D = c.embed_dim; e->FF = c.ffn_dim; e->heads = c.heads; e->dh = c.heads ? c.embed_dim / c.heads : 0;
+  e->depth = c.depth; e->K = c.num_keypoints; e->DC = c.deconv_channels;
+  e->PK = 3 * c.patch * c.patch;
+  e->max_b2 = 2 * c.max_batch;
+  e->params.clear();
+  e->index.clear();
+  const int D = e->D, FF = e->FF, DC = e->DC, K = e->K, prec = e->prec;
+  const int64_t M = (int64_t)e->tokens * e->max_b2;
+  Bump b;
+
+  // ---- raw fp32 parameters, by MMPose state_dict name ----
+  if (e->depth > 0) {
+    add_param(e, b, "backbone.patch_embed.projection.weight", (int64_t)D * e->PK, 0);
+    add_param(e, b, "backbone.patch_embed.projection.bias", D, 0);
+    add_param(e, b, "backbone.pos_embed", (int64_t)e->tokens * D, 0);
+    for (int l = 0; l < e->depth; ++l) {
+      const std::string p = "backbone.layers." + std::to_string(l) + ".";
+      add_param(e, b, p + "ln1.weight", D, 0); add_param(e, b, p + "ln1.bias", D, 0);
+      add_param(e, b, p + "attn.qkv.weight", (int64_t)3 * D * D, 0); add_param(e, b, p + "attn.qkv.bias", 3 * D, 0);
+      add_param(e, b, p + "attn.proj.weight", (int64_t)D * D, 0); add_param(e, b, p + "attn.proj.bias", D, 0);
+      add_param(e, b, p + "ln2.weight", D, 0); add_param(e, b, p + "ln2.bias", D, 0);
+      add_param(e, b, p + "ffn.layers.0.0.weight", (int64_t)FF * D, 0); add_param(e, b, p + "ffn.layers.0.0.bias", FF, 0);
+      add_param(e, b, p + "ffn.layers.1.weight", (int64_t)D * FF, 0); add_param(e, b, p + "ffn.layers.1.bias", D, 0);
+    }
+    add_param(e, b, "backbone.ln1.weight", D, 0); add_param(e, b, "backbone.ln1.bias", D, 0);
+  }
+  if (DC > 0) {
+    int cin = D;
+    for (int i = 0; i < 2; ++i) {
+      add_param(e, b, "head.deconv_layers." + std::to_string(3 * i) + ".weight", (int64_t)cin * DC * 16, 1);
+      const std::string bn = "head.deconv_layers." + std::to_string(3 * i + 1) + ".";
+      for (const char* s : {"weight", "bias", "running_mean", "running_var"}) add_param(e, b, bn + s, DC, 1);
+      cin = DC;
+    }
+    add_param(e, b, "head.final_layer.weight", (int64_t)K * DC, 1);
+    add_param(e, b, "head.final_layer.bias", K, 1);
+    for (int br = 0; br < 4; ++br) {
+      const std::string p = std::string("head.") + kBranches[br] + "_layers.";
+      for (int j = 0; j < 3; ++j) {
+        add_param(e, b, p + std::to_string(4 * j) + ".weight", (int64_t)D * D * 9, 1);
+        add_param(e, b, p + std::to_string(4 * j) + ".bias", D, 1);
+        for (const char* s : {"weight", "bias", "running_mean", "running_var"})
+          add_param(e, b, p + std::to_string(4 * j + 1) + "." + s, D, 1);
+      }
+      add_param(e, b, p + "12.weight", (int64_t)K * D, 1);
+      add_param(e, b, p + "12.bias", K, 1);
+    }
+  }
+
+  // ---- packed weights ----
+  if (e->depth > 0) {
+    e->w_patch = b.take(pp_operand_bytes(prec, D, e->PK));
+    e->layers.resize(e->depth);
+    for (auto& L : e->layers) {
+      L.wqkv = b.take(pp_operand_bytes(prec, 3 * D, D));
+      L.wproj = b.take(pp_operand_bytes(prec, D, D));
+      L.wfc1 = b.take(pp_operand_bytes(prec, FF, D));
+      L.wfc2 = b.take(pp_operand_bytes(prec, D, FF));
+    }
+  }
+  if (DC > 0) {
+    for (int i = 0; i < 2; ++i) {
+      const int cin = i == 0 ? D : DC;
+      for (int ph = 0; ph < 4; ++ph) e->w_dc[i][ph] = b.take(pp_operand_bytes(prec, DC, 4 * cin));
+      e->dc_scale[i] = b.take(DC * sizeof(float));
+      e->dc_shift[i] = b.take(DC * sizeof(float));
+    }
+    e->w_final = b.take(pp_operand_bytes(prec, K, DC));
+    e->w_c1 = b.take(pp_operand_bytes(prec, 4 * D, 9 * D));
+    for (int br = 0; br < 4; ++br) {
+      e->w_c2[br] = b.take(pp_operand_bytes(prec, D, 9 * D));
+      e->w_c3[br] = b.take(pp_operand_bytes(prec, D, 9 * D));
+    }
+    for (int j = 0; j < 3; ++j) {
+      e->c_scale[j] = b.take((size_t)4 * D * sizeof(float));
+      e->c_shift[j] = b.take((size_t)4 * D * sizeof(float));
+    }
+    e->tail_w = b.take((size_t)4 * K * D * sizeof(float));
+    e->tail_b = b.take((size_t)4 * K * sizeof(float));
+    e->pack_tmp = b.take((size_t)4 * D * 9 * D * sizeof(float));
+  }
+
+  // ---- activations ----
+  if (e->depth > 0) {
+    e->x = b.take((size_t)M * D * sizeof(float));
+    e->a_op = b.take(pp_operand_bytes(prec, M, e->PK > D ? e->PK : D));
+    e->qkv = b.take((size_t)M * 3 * D * sizeof(float));
+    e->h_op = b.take(pp_operand_bytes(prec, M, FF));
+  }
+  e->feat_op = b.take(pp_operand_bytes(prec, M, D));
+  e->feat_f32 = b.take((size_t)M * D * sizeof(float));
+  if (DC > 0) {
+    size_t g = pp_operand_bytes(prec, M, 9 * D);
+    const size_t g2 = pp_operand_bytes(prec, 4 * M, 4 * DC), g1 = pp_operand_bytes(prec, M, 4 * D);
+    if (g2 > g) g = g2;
+    if (g1 > g) g = g1;
+    e->g_op = b.take(g);
+    e->d1_op = b.take(pp_operand_bytes(prec, 4 * M, DC));
+    e->d2_op = b.take(pp_operand_bytes(prec, 16 * M, DC));
+    e->logits = b.take((size_t)e->max_b2 * K * 16 * e->tokens * sizeof(float));
+    e->c_f32 = b.take((size_t)M * 4 * D * sizeof(float));
+    e->pool_op = b.take(pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 4 * D));
+    e->scal = b.take((size_t)e->max_b2 * 4 * K * sizeof(float));
+  }
+  return b.off;
+}
+
+static int validate_cfg(const pp_engine_cfg* c) {
+  PP_REQUIRE(c != nullptr, PP_ERR_INVALID, "engine cfg must be non-NULL");
+  PP_REQUIRE(c->precision >= PP_PREC_FP16X3 && c->precision <= PP_PREC_FP32_SIMT, PP_ERR_INVALID, "bad precision %d",
+             c->precision);
+  PP_REQUIRE(c->max_batch >= 1 && c->max_batch <= 8192, PP_ERR_INVALID, "max_batch %d outside [1, 8192]", c->max_batch);
+  PP_REQUIRE(c->patch > 0 && c->patch % 4 == 0 && c->patch_pad >= 0 && c->img_h >= c->patch && c->img_w >= c->patch,
+             PP_ERR_INVALID, "bad image / patch geometry %dx%d patch %d pad %d", c->img_h, c->img_w, c->patch, c->patch_pad);
+  PP_REQUIRE(c->depth >= 0 && c->depth <= 64, PP_ERR_INVALID, "depth %d", c->depth);
+  PP_REQUIRE(c->embed_dim == 384 || c->embed_dim == 768, PP_ERR_UNSUPPORTED, "embed_dim %d not built (384, 768)",
+             c->embed_dim);
+  if (c->depth > 0) {
+    PP_REQUIRE(c->heads > 0 && c->embed_dim % c->heads == 0 && (c->embed_dim / c->heads == 32 || c->embed_dim / c->heads == 64),
+               PP_ERR_UNSUPPORTED, "heads %d: head width must be 32 or 64", c->heads);
+    PP_REQUIRE(c->ffn_dim > 0 && c->ffn_dim % 64 == 0, PP_ERR_UNSUPPORTED, "ffn_dim %d must be a multiple of 64", c->ffn_dim);
+    PP_REQUIRE((3 * c->patch * c->patch) % 64 == 0, PP_ERR_UNSUPPORTED, "patch %d: 3*patch^2 must be a multiple of 64", c->patch);
+  }
+  PP_REQUIRE(c->depth > 0 || c->deconv_channels > 0, PP_ERR_INVALID, "engine has neither a backbone nor a head");
+  if (c->deconv_channels > 0) {
+    PP_REQUIRE(c->deconv_channels % 64 == 0, PP_ERR_UNSUPPORTED, "deconv_channels %d must be a multiple of 64",
+               c->deconv_channels);
+    PP_REQUIRE(c->num_keypoints >= 1 && c->num_keypoints <= PP_MAX_KEYPOINTS, PP_ERR_INVALID, "num_keypoints %d outside [1, %d]",
+               c->num_keypoints, PP_MAX_KEYPOINTS);
+    const int gh = (c->img_h + 2 * c->patch_pad - c->patch) / c->patch + 1, gw = (c->img_w + 2 * c->patch_pad - c->patch) / c->patch + 1;
+    PP_REQUIRE(gh == 16 && gw == 12, PP_ERR_UNSUPPORTED,
+               "ProbMapHead pools (4,3),(2,2),(2,2) (probmap_head.py:264) need a 16x12 feature map, got %dx%d", gh, gw);
+    PP_REQUIRE(c->temperature > 0.f, PP_ERR_INVALID, "temperature must be > 0");
+  }
+  return PP_OK;
+}
+
+static pp_gemm_args gemm_args(const pp_engine* e, int64_t m, int n, int k, const void* a, const void* w) {
+  pp_gemm_args g = {};
+  g.precision = e->prec; g.m = (int)m; g.n = n; g.k = k; g.a = a; g.w = w;
+  g.act = PP_ACT_NONE; g.out_kind = PP_OUT_F32; g.ldd = n;
+  return g;
+}
+
+#define PP_TRY(expr)            \
+  do {                          \
+    const int _rc = (expr);     \
+    if (_rc != PP_OK) return _rc; \
+  } while (0)
+
+static int to_operand(const pp_engine* e, const float* src, int64_t rows, int64_t k, size_t dst_off, cudaStream_t st) {
+  return pp_operand_from_f32(e->prec, src, rows, k, k, e->at<>(dst_off), st);
+}
+
+// ---- forward pieces ---------------------------------------------------------------------------
+static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int batch, int passes, bool want_f32,
+                        cudaStream_t st) {
+  const int D = e->D, FF = e->FF, prec = e->prec;
+  const int64_t M = (int64_t)passes * batch * e->tokens;
+  PatchifyParams pp_;
+  pp_.u8_bgr = u8; pp_.x_f32 = xf; pp_.batch = batch; pp_.passes = passes;
+  pp_.img_h = e->cfg.img_h; pp_.img_w = e->cfg.img_w; pp_.patch = e->cfg.patch; pp_.pad = e->cfg.patch_pad;
+  pp_.gh = e->gh; pp_.gw = e->gw;
+  for (int c = 0; c < 3; ++c) { pp_.mean[c] = e->cfg.mean[c]; pp_.inv_std[c] = 1.0f / e->cfg.std[c]; }
+  PP_TRY(launch_patchify(prec, pp_, e->at<>(e->a_op), st));
+  {
+    pp_gemm_args g = gemm_args(e, M, D, e->PK, e->at<>(e->a_op), e->at<>(e->w_patch));
+    g.shift = e->P("backbone.patch_embed.projection.bias");
+    g.residual = e->P("backbone.pos_embed"); g.res_mod = e->tokens;
+    g.d = e->at<>(e->x);
+    PP_TRY(gemm_dispatch(g, st));
+  }
+  float* x = e->at<float>(e->x);
+  for (int l = 0; l < e->depth; ++l) {
+    const std::string p = "backbone.layers." + std::to_string(l) + ".";
+    const pp_engine::Layer& L = e->layers[l];
+    PP_TRY(launch_layernorm(prec, x, e->P(p + "ln1.weight"), e->P(p + "ln1.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
+                            nullptr, st));
+    pp_gemm_args g = gemm_args(e, M, 3 * D, D, e->at<>(e->a_op), e->at<>(L.wqkv));
+    g.shift = e->P(p + "attn.qkv.bias"); g.d = e->at<>(e->qkv);
+    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st));
+    g = gemm_args(e, M, D, D, e->at<>(e->a_op), e->at<>(L.wproj));
+    g.shift = e->P(p + "attn.proj.bias"); g.residual = x; g.d = x;
+    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(launch_layernorm(prec, x, e->P(p + "ln2.weight"), e->P(p + "ln2.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
+                            nullptr, st));
+    g = gemm_args(e, M, FF, D, e->at<>(e->a_op), e->at<>(L.wfc1));
+    g.shift = e->P(p + "ffn.layers.0.0.bias"); g.act = PP_ACT_GELU; g.out_kind = PP_OUT_OPERAND; g.ldd = FF;
+    g.d = e->at<>(e->h_op);
+    PP_TRY(gemm_dispatch(g, st));
+    g = gemm_args(e, M, D, FF, e->at<>(e->h_op), e->at<>(L.wfc2));
+    g.shift = e->P(p + "ffn.layers.1.bias"); g.residual = x; g.d = x;
+    PP_TRY(gemm_dispatch(g, st));
+  }
+  PP_TRY(launch_layernorm(prec, x, e->P("backbone.ln1.weight"), e->P("backbone.ln1.bias"), e->cfg.ln_eps, M, D,
+                          e->at<>(e->feat_op), want_f32 ? e->at<float>(e->feat_f32) : nullptr, st));
+  return PP_OK;
+}
+
+// feat_op (n_img * tokens, D) -> logits (n_img, K, 16 * tokens), scalars (n_img, 4, K)
+static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cudaStream_t st) {
+  const int D = e->D, DC = e->DC, K = e->K, prec = e->prec;
+  const int64_t M = (int64_t)n_img * e->tokens;
+  // --- heatmap branch: two stride-2 deconvs as 4 sub-pixel phase GEMMs each, then the 1x1 conv ---
+  for (int i = 0; i < 2; ++i) {
+    const int cin = i == 0 ? D : DC, h = e->gh << i, w = e->gw << i;
+    const int64_t rows = (int64_t)n_img * h * w;
+    const void* src = i == 0 ? e->at<>(e->feat_op) : e->at<>(e->d1_op);
+    void* dst = i == 0 ? e->at<>(e->d1_op) : e->at<>(e->d2_op);
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      GatherParams gp = {};
+      gp.batch = n_img; gp.h = h; gp.w = w; gp.c = cin; gp.src_c = cin; gp.c_off = 0; gp.ntaps = 4;
+      for (int t = 0; t < 4; ++t) {
+        int kk;
+        deconv_tap(py, t >> 1, &gp.dy[t], &kk);
+        deconv_tap(px, t & 1, &gp.dx[t], &kk);
+      }
+      PP_TRY(launch_gather_taps(prec, gp, src, e->at<>(e->g_op), st));
+      pp_gemm_args g = gemm_args(e, rows, DC, 4 * cin, e->at<>(e->g_op), e->at<>(e->w_dc[i][ph]));
+      g.scale = e->at<float>(e->dc_scale[i]); g.shift = e->at<float>(e->dc_shift[i]); g.act = PP_ACT_RELU;
+      g.out_kind = PP_OUT_OPERAND; g.ldd = DC; g.d = dst;
+      g.up_hin = h; g.up_win = w; g.up_py = py; g.up_px = px;
+      PP_TRY(gemm_dispatch(g, st));
+    }
+  }
+  {
+    pp_gemm_args g = gemm_args(e, 16 * M, K, DC, e->at<>(e->d2_op), e->at<>(e->w_final));
+    g.shift = e->P("head.final_layer.bias"); g.out_kind = PP_OUT_PLANES; g.plane = 16 * e->tokens; g.d = logits;
+    PP_TRY(gemm_dispatch(g, st));
+  }
+  // --- four scalar branches; the first conv of all four shares its input -> one GEMM, N = 4 D ---
+  GatherParams g3 = {};
+  g3.ntaps = 9;
+  for (int t = 0; t < 9; ++t) { g3.dy[t] = t / 3 - 1; g3.dx[t] = t % 3 - 1; }
+  g3.batch = n_img; g3.h = e->gh; g3.w = e->gw; g3.c = D; g3.src_c = D; g3.c_off = 0;
+  PP_TRY(launch_gather_taps(prec, g3, e->at<>(e->feat_op), e->at<>(e->g_op), st));
+  {
+    pp_gemm_args g = gemm_args(e, M, 4 * D, 9 * D, e->at<>(e->g_op), e->at<>(e->w_c1));
+    g.scale = e->at<float>(e->c_scale[0]); g.shift = e->at<float>(e->c_shift[0]); g.d = e->at<>(e->c_f32);
+    PP_TRY(gemm_dispatch(g, st));
+  }
+  int h = e->gh, w = e->gw;
+  const int pool[3][2] = {{4, 3}, {2, 2}, {2, 2}};  // probmap_head.py:264
+  for (int j = 1; j < 3; ++j) {
+    PP_TRY(launch_pool_relu(prec, e->at<float>(e->c_f32), n_img, h, w, 4 * D, pool[j - 1][0], pool[j - 1][1],
+                            e->at<>(e->pool_op), st));
+    h /= pool[j - 1][0]; w /= pool[j - 1][1];
+    const int64_t rows = (int64_t)n_img * h * w;
+    for (int br = 0; br < 4; ++br) {
+      g3.h = h; g3.w = w; g3.src_c = 4 * D; g3.c_off = br * D;
+      PP_TRY(launch_gather_taps(prec, g3, e->at<>(e->pool_op), e->at<>(e->g_op), st));
+      pp_gemm_args g = gemm_args(e, rows, D, 9 * D, e->at<>(e->g_op), e->at<>(j == 1 ? e->w_c2[br] : e->w_c3[br]));
+      g.scale = e->at<float>(e->c_scale[j]) + br * D; g.shift = e->at<float>(e->c_shift[j]) + br * D;
+      g.ldd = 4 * D; g.d = e->at<float>(e->c_f32) + br * D;
+      PP_TRY(gemm_dispatch(g, st));
+    }
+  }
+  PP_TRY(launch_branch_tail(e->at<float>(e->c_f32), n_img, D, K, e->at<float>(e->tail_w), e->at<float>(e->tail_b), scalars, st));
+  return PP_OK;
+}
+
+static int check_batch(const pp_engine* e, int batch, int passes, const char* what) {
+  PP_REQUIRE(e != nullptr, PP_ERR_INVALID, "%s: engine is NULL", what);
+  PP_REQUIRE(batch >= 0 && (int64_t)batch * passes <= e->max_b2, PP_ERR_INVALID,
+             "%s: batch %d (x%d passes) exceeds the engine's max_batch %d", what, batch, passes, e->cfg.max_batch);
+  return PP_OK;
+}
+
+}  // namespace pp
+
+// =================================== C ABI ====================================================
+using namespace pp;
+
+extern "C" size_t pp_engine_workspace_bytes(const pp_engine_cfg* cfg) {
+  if (validate_cfg(cfg) != PP_OK) return 0;
+  pp_engine tmp;
+  tmp.cfg = *cfg;
+  return plan(&tmp);
+}
+
+extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_t workspace_bytes, pp_engine** out) {
+  PP_REQUIRE(out != nullptr, PP_ERR_INVALID, "pp_engine_create: out is NULL");
+  *out = nullptr;
+  PP_TRY(validate_cfg(cfg));
+  PP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, PP_ERR_INVALID,
+             "pp_engine_create: workspace must be non-NULL and 1024-byte aligned");
+  pp_engine* e = new pp_engine();
+  e->cfg = *cfg;
+  const size_t need = plan(e);
+  if (workspace_bytes < need) {
+    set_error("pp_engine_create: workspace of %zu bytes is smaller than the %zu required", workspace_bytes, need);
+    delete e;
+    return PP_ERR_INVALID;
+  }
+  e->base = reinterpret_cast<uint8_t*>(workspace);
+  e->bytes = workspace_bytes;
+  *out = e;
+  return PP_OK;
+}
+
+extern "C" void pp_engine_destroy(pp_engine* e) { delete e; }
+
+extern "C" int pp_engine_load(pp_engine* e, const char* name, const float* data, int64_t numel, void* stream) {
+  PP_REQUIRE(e && name && data, PP_ERR_INVALID, "pp_engine_load: NULL argument");
+  const std::string n(name);
+  if (n.size() >= 19 && n.compare(n.size() - 19, 19, "num_batches_tracked") == 0) return PP_OK;  // BN bookkeeping, unused
+  auto it = e->index.find(n);
+  PP_REQUIRE(it != e->index.end(), PP_ERR_INVALID, "pp_engine_load: unknown parameter '%s'", name);
+  Param& p = e->params[it->second];
+  PP_REQUIRE(p.numel == numel, PP_ERR_INVALID, "pp_engine_load: '%s' has %lld elements, expected %lld", name,
+             (long long)numel, (long long)p.numel);
+  PP_CHECK_CUDA(cudaMemcpyAsync(e->base + p.off, data, (size_t)numel * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  p.loaded = true;
+  e->backbone_ready = e->head_ready = false;  // finalize again
+  return PP_OK;
+}
+
+extern "C" int pp_engine_finalize(pp_engine* e, void* stream) {
+  PP_REQUIRE(e != nullptr, PP_ERR_INVALID, "pp_engine_finalize: engine is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  int loaded[2] = {0, 0}, total[2] = {0, 0};
+  const Param* missing[2] = {nullptr, nullptr};
+  for (const Param& p : e->params) {
+    ++total[p.group];
+    if (p.loaded) ++loaded[p.group];
+    else if (!missing[p.group]) missing[p.group] = &p;
+  }
+  for (int g = 0; g < 2; ++g)
+    PP_REQUIRE(loaded[g] == 0 || loaded[g] == total[g], PP_ERR_STATE,
+               "pp_engine_finalize: %d of %d %s parameters loaded; first missing '%s'", loaded[g], total[g],
+               g ? "head" : "backbone", missing[g]->name.c_str());
+  PP_REQUIRE(loaded[0] + loaded[1] > 0, PP_ERR_STATE, "pp_engine_finalize: no parameters loaded");
+  const int D = e->D, FF = e->FF, DC = e->DC, K = e->K;
+  if (total[0] > 0 && loaded[0] == total[0]) {
+    PP_TRY(to_operand(e, e->P("backbone.patch_embed.projection.weight"), D, e->PK, e->w_patch, st));
+    for (int l = 0; l < e->depth; ++l) {
+      const std::string p = "backbone.layers." + std::to_string(l) + ".";
+      PP_TRY(to_operand(e, e->P(p + "attn.qkv.weight"), 3 * D, D, e->layers[l].wqkv, st));
+      PP_TRY(to_operand(e, e->P(p + "attn.proj.weight"), D, D, e->layers[l].wproj, st));
+      PP_TRY(to_operand(e, e->P(p + "ffn.layers.0.0.weight"), FF, D, e->layers[l].wfc1, st));
+      PP_TRY(to_operand(e, e->P(p + "ffn.layers.1.weight"), D, FF, e->layers[l].wfc2, st));
+    }
+    e->backbone_ready = true;
+  }
+  if (total[1] > 0 && loaded[1] == total[1]) {
+    float* tmp = e->at<float>(e->pack_tmp);
+    for (int i = 0; i < 2; ++i) {
+      const int cin = i == 0 ? D : DC;
+      const std::string w = "head.deconv_layers." + std::to_string(3 * i) + ".weight";
+      const std::string bn = "head.deconv_layers." + std::to_string(3 * i + 1) + ".";
+      for (int ph = 0; ph < 4; ++ph) {
+        PP_TRY(launch_pack_deconv_phase(e->P(w), cin, DC, ph >> 1, ph & 1, tmp, st));
+        PP_TRY(to_operand(e, tmp, DC, 4 * cin, e->w_dc[i][ph], st));
+      }
+      PP_TRY(launch_fold_bn(e->P(bn + "weight"), e->P(bn + "bias"), e->P(bn + "running_mean"), e->P(bn + "running_var"),
+                            nullptr, e->cfg.bn_eps, DC, e->at<float>(e->dc_scale[i]), e->at<float>(e->dc_shift[i]), st));
+    }
+    PP_TRY(to_operand(e, e->P("head.final_layer.weight"), K, DC, e->w_final, st));
+    for (int br = 0; br < 4; ++br) {
+      const std::string p = std::string("head.") + kBranches[br] + "_layers.";
+      PP_TRY(launch_pack_conv3x3(e->P(p + "0.weight"), D, D, tmp + (size_t)br * D * 9 * D, st));
+      for (int j = 0; j < 3; ++j) {
+        const std::string bn = p + std::to_string(4 * j + 1) + ".";
+        PP_TRY(launch_fold_bn(e->P(bn + "weight"), e->P(bn + "bias"), e->P(bn + "running_mean"), e->P(bn + "running_var"),
+                              e->P(p + std::to_string(4 * j) + ".bias"), e->cfg.bn_eps, D,
+                              e->at<float>(e->c_scale[j]) + br * D, e->at<float>(e->c_shift[j]) + br * D, st));
+      }
+      PP_CHECK_CUDA(cudaMemcpyAsync(e->at<float>(e->tail_w) + (size_t)br * K * D, e->P(p + "12.weight"),
+                                    (size_t)K * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PP_CHECK_CUDA(cudaMemcpyAsync(e->at<float>(e->tail_b) + (size_t)br * K, e->P(p + "12.bias"), (size_t)K * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    PP_TRY(to_operand(e, tmp, 4 * D, 9 * D, e->w_c1, st));
+    for (int br = 0; br < 4; ++br) {
+      const std::string p = std::string("head.") + kBranches[br] + "_layers.";
+      PP_TRY(launch_pack_conv3x3(e->P(p + "4.weight"), D, D, tmp, st));
+      PP_TRY(to_operand(e, tmp, D, 9 * D, e->w_c2[br], st));
+      PP_TRY(launch_pack_conv3x3(e->P(p + "8.weight"), D, D, tmp, st));
+      PP_TRY(to_operand(e, tmp, D, 9 * D, e->w_c3[br], st));
+    }
+    e->head_ready = true;
+  }
+  return PP_OK;
+}
+
+extern "C" int pp_engine_backbone(pp_engine* e, const float* x, int32_t batch, float* feat_nchw, void* stream) {
+  PP_TRY(check_batch(e, batch, 1, "pp_engine_backbone"));
+  PP_REQUIRE(e->backbone_ready, PP_ERR_STATE, "pp_engine_backbone: backbone weights not loaded / finalized");
+  PP_REQUIRE(batch == 0 || (x && feat_nchw), PP_ERR_INVALID, "pp_engine_backbone: NULL tensor");
+  const int64_t before = g_launch_count;
+  if (batch > 0) {
+    PP_TRY(run_backbone(e, nullptr, x, batch, 1, true, (cudaStream_t)stream));
+    PP_TRY(launch_rows_to_nchw(e->at<float>(e->feat_f32), batch, e->tokens, e->D, feat_nchw, (cudaStream_t)stream));
+  }
+  e->last_launches = g_launch_count - before;
+  return PP_OK;
+}
+
+extern "C" int pp_engine_head(pp_engine* e, const float* feat_nchw, int32_t batch, float* heat_logits, float* scalars,
+                              void* stream) {
+  PP_TRY(check_batch(e, batch, 1, "pp_engine_head"));
+  PP_REQUIRE(e->head_ready, PP_ERR_STATE, "pp_engine_head: head weights not loaded / finalized");
+  PP_REQUIRE(batch == 0 || (feat_nchw && heat_logits && scalars), PP_ERR_INVALID, "pp_engine_head: NULL tensor");
+  const int64_t before = g_launch_count;
+  if (batch > 0) {
+    PP_TRY(launch_nchw_to_operand(e->prec, feat_nchw, batch, e->tokens, e->D, e->at<>(e->feat_op), (cudaStream_t)stream));
+    PP_TRY(run_head(e, batch, heat_logits, scalars, (cudaStream_t)stream));
+  }
+  e->last_launches = g_launch_count - before;
+  return PP_OK;
+}
+
+extern "C" int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const float* x_f32, int32_t batch,
+                               int32_t flip_test, const int32_t* flip_indices, float* records, float* merged_out,
+                               void* stream) {
+  const int passes = flip_test ? 2 : 1;
+  PP_TRY(check_batch(e, batch, passes, "pp_engine_infer"));
+  PP_REQUIRE(e->backbone_ready && e->head_ready, PP_ERR_STATE,
+             "pp_engine_infer: needs backbone and head weights loaded and finalized");
+  PP_REQUIRE(batch == 0 || records, PP_ERR_INVALID, "pp_engine_infer: records is NULL");
+  PP_REQUIRE(!flip_test || flip_indices, PP_ERR_INVALID, "pp_engine_infer: flip_test needs flip_indices");
+  const int64_t before = g_launch_count;
+  if (batch > 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PP_TRY(run_backbone(e, crops_u8_bgr, x_f32, batch, passes, false, st));
+    float* logits = e->at<float>(e->logits);
+    float* scal = e->at<float>(e->scal);
+    PP_TRY(run_head(e, passes * batch, logits, scal, st));
+    pp_decode_cfg dc;
+    dc.num_keypoints = e->K; dc.height = 4 * e->gh; dc.width = 4 * e->gw; dc.input_is_logits = 1;
+    dc.temperature = e->cfg.temperature; dc.normalize = e->cfg.normalize; dc.error_divisor = 0.f;
+    const size_t map_stride = (size_t)batch * e->K * 16 * e->tokens, sc_stride = (size_t)batch * 4 * e->K;
+    PP_TRY(pp_decode(&dc, logits, flip_test ? logits + map_stride : nullptr, flip_indices, scal,
+                     flip_test ? scal + sc_stride : nullptr, batch, records, merged_out, stream));
+  }
+  e->last_launches = g_launch_count - before;
+  return PP_OK;
+}
+
+extern "C" int64_t pp_engine_last_launch_count(const pp_engine* e) { return e ? e->last_launches : 0; }

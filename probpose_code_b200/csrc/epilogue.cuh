@@ -15,6 +15,7 @@ struct EpiParams {
   int m, n;
   int act, out_kind, ldd, plane;
   int up_hin, up_win, up_py, up_px;
+  int res_mod;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -46,7 +47,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int m, int n0, flo
 
   if (e.out_kind == PP_OUT_F32) {
     float* drow = reinterpret_cast<float*>(e.d) + orow * e.ldd + n0;
-    const float* rrow = e.residual ? e.residual + orow * e.ldd + n0 : nullptr;
+    const float* rrow = e.residual ? e.residual + (e.res_mod > 0 ? orow % e.res_mod : orow) * e.ldd + n0 : nullptr;
     if (full && (e.ldd & 3) == 0) {
 #pragma unroll
       for (int c = 0; c < NC; c += 4) {

@@ -83,27 +83,37 @@ extern "C" int pp_operand_from_f32(int32_t precision, const float* src, int64_t 
   return PP_OK;
 }
 
+namespace pp {
+
+int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st) {
+  if (a.m == 0) return PP_OK;
+  EpiParams e;
+  e.scale = a.scale; e.shift = a.shift; e.residual = a.residual; e.d = a.d;
+  e.m = a.m; e.n = a.n; e.act = a.act; e.out_kind = a.out_kind; e.ldd = a.ldd; e.plane = a.plane;
+  e.up_hin = a.up_hin; e.up_win = a.up_win; e.up_py = a.up_py; e.up_px = a.up_px;
+  e.res_mod = a.res_mod;
+  if (a.precision == PP_PREC_FP32_SIMT) {
+    dim3 grid((a.n + kSB - 1) / kSB, (a.m + kSB - 1) / kSB);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a.a), reinterpret_cast<const float*>(a.w), a.k, e);
+    count_launch();
+    PP_CHECK_CUDA(cudaGetLastError());
+    return PP_OK;
+  }
+  return gemm_tc_launch(a, e, a.tile_n, st);
+}
+
+}  // namespace pp
+
 extern "C" int pp_gemm(const pp_gemm_args* a, void* stream) {
   using namespace pp;
   PP_REQUIRE(a && a->a && a->w && a->d, PP_ERR_INVALID, "pp_gemm: NULL argument");
+  PP_REQUIRE(a->precision >= PP_PREC_FP16X3 && a->precision <= PP_PREC_FP32_SIMT, PP_ERR_INVALID, "pp_gemm: bad precision %d", a->precision);
   PP_REQUIRE(a->m >= 0 && a->n > 0 && a->k > 0, PP_ERR_INVALID, "pp_gemm: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
   PP_REQUIRE(a->out_kind >= PP_OUT_F32 && a->out_kind <= PP_OUT_PLANES, PP_ERR_INVALID, "pp_gemm: bad out_kind %d", a->out_kind);
   PP_REQUIRE(a->out_kind != PP_OUT_PLANES || a->plane > 0, PP_ERR_INVALID, "pp_gemm: PP_OUT_PLANES needs plane > 0");
   PP_REQUIRE(a->out_kind == PP_OUT_PLANES || a->ldd >= a->n, PP_ERR_INVALID, "pp_gemm: ldd=%d < n=%d", a->ldd, a->n);
   PP_REQUIRE(a->out_kind != PP_OUT_OPERAND || (a->ldd % 4 == 0 && a->residual == nullptr), PP_ERR_INVALID,
              "pp_gemm: operand output needs ldd %% 4 == 0 and no residual");
-  if (a->m == 0) return PP_OK;
-  EpiParams e;
-  e.scale = a->scale; e.shift = a->shift; e.residual = a->residual; e.d = a->d;
-  e.m = a->m; e.n = a->n; e.act = a->act; e.out_kind = a->out_kind; e.ldd = a->ldd; e.plane = a->plane;
-  e.up_hin = a->up_hin; e.up_win = a->up_win; e.up_py = a->up_py; e.up_px = a->up_px;
-  if (a->precision == PP_PREC_FP32_SIMT) {
-    dim3 grid((a->n + kSB - 1) / kSB, (a->m + kSB - 1) / kSB);
-    gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(a->a),
-                                                             reinterpret_cast<const float*>(a->w), a->k, e);
-    count_launch();
-    PP_CHECK_CUDA(cudaGetLastError());
-    return PP_OK;
-  }
-  return gemm_tc_launch(*a, e, a->tile_n, (cudaStream_t)stream);
+  PP_REQUIRE(a->res_mod >= 0, PP_ERR_INVALID, "pp_gemm: res_mod=%d", a->res_mod);
+  return gemm_dispatch(*a, (cudaStream_t)stream);
 }

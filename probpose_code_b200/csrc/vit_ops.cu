@@ -1,0 +1,265 @@
+// Non-GEMM kernels of the ViT backbone: patch extraction (+ preprocessing, + mirrored pass),
+// LayerNorm -> GEMM operand, global attention, layout changes.
+//
+// Reference semantics: PoseDataPreprocessor (data_preprocessor.py:79-104), mmpretrain 1.2.0
+// VisionTransformer / MultiheadAttention (config :56-67), mmcv PatchEmbed (in-tree twin
+// mmpose/models/utils/transformer.py:153-245), flipped pass topdown.py:109-112.
+#include "engine_ops.cuh"
+
+#include <math.h>
+
+namespace pp {
+
+// ---- patch extraction --------------------------------------------------------------------
+template <int PREC>
+__global__ void __launch_bounds__(256) patchify_kernel(const PatchifyParams p, void* a_op) {
+  const int P = p.patch, PP = P * P, K = 3 * PP, K4 = K / 4;
+  const int tokens = p.gh * p.gw;
+  const int64_t total = (int64_t)p.passes * p.batch * tokens * K4;
+  const size_t plane = (size_t)p.img_h * p.img_w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K4) * 4;
+    const int64_t m = i / K4;
+    const int tok = (int)(m % tokens);
+    const int bb = (int)(m / tokens);
+    const int pass = bb / p.batch, b = bb % p.batch;
+    const int c = k / PP, ky = (k % PP) / P, kx = k % P;
+    const int y = (tok / p.gw) * P - p.pad + ky;
+    const int x0 = (tok % p.gw) * P - p.pad + kx;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= 0 && y < p.img_h) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int x = x0 + e;                      // column in the (possibly mirrored) image
+        if (x < 0 || x >= p.img_w) continue; // zero border of the NORMALISED image
+        if (pass) x = p.img_w - 1 - x;
+        if (p.u8_bgr) {
+          const float raw = (float)p.u8_bgr[((size_t)b * 3 + (2 - c)) * plane + (size_t)y * p.img_w + x];
+          v[e] = (raw - p.mean[c]) * p.inv_std[c];
+        } else {
+          v[e] = p.x_f32[((size_t)b * 3 + c) * plane + (size_t)y * p.img_w + x];
+        }
+      }
+    }
+    store_operand4<PREC>(a_op, m, k, K, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t st) {
+  PP_REQUIRE((p.u8_bgr != nullptr) != (p.x_f32 != nullptr), PP_ERR_INVALID,
+             "exactly one of crops_u8_bgr and x_f32 must be given");
+  PP_REQUIRE(p.patch % 4 == 0, PP_ERR_UNSUPPORTED, "patch size %d not a multiple of 4", p.patch);
+  const int64_t total = (int64_t)p.passes * p.batch * p.gh * p.gw * (3 * p.patch * p.patch / 4);
+  if (total == 0) return PP_OK;
+  const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  PP_DISPATCH_PREC(prec, (patchify_kernel<PREC><<<grid, 256, 0, st>>>(p, a_op)));
+  count_launch();
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---- LayerNorm ----------------------------------------------------------------------------
+// One warp per row; the row lives in registers (NV float4 per lane, d = 128 * NV).
+// Two-pass mean / variance in fp32 like ATen's CPU and CUDA kernels.
+template <int PREC, int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int64_t rows,
+                                                        void* out_op, float* out_f32) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (lane + 32 * i) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+    const float4 b = *reinterpret_cast<const float4*>(beta + col);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out_op) store_operand4<PREC>(out_op, row, col, D, o);
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + col) = o;
+  }
+}
+
+int launch_layernorm(int prec, const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
+                     void* out_op, float* out_f32, cudaStream_t st) {
+  PP_REQUIRE(d == 384 || d == 768, PP_ERR_UNSUPPORTED, "LayerNorm width %d not built (384, 768)", d);
+  if (rows == 0) return PP_OK;
+  const int grid = (int)((rows + 7) / 8);
+  if (d == 384) {
+    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 3><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32)));
+  } else {
+    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 6><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32)));
+  }
+  count_launch();
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---- attention (fp32 CUDA-core version) ---------------------------------------------------
+// One CTA per (image, head); K and V of the head sit in shared memory, each thread owns one
+// query row and walks all keys with a running-max softmax (exact up to fp32 rounding).
+template <int PREC, int DH>
+__global__ void __launch_bounds__(256) attention_simt_kernel(const float* __restrict__ qkv, int n, int heads,
+                                                             void* out_op) {
+  extern __shared__ __align__(16) float att_smem[];
+  float* sK = att_smem;
+  float* sV = att_smem + (size_t)n * DH;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int D = heads * DH;
+  const float* base = qkv + (size_t)b * n * 3 * D + h * DH;
+  for (int i = threadIdx.x; i < n * (DH / 4); i += blockDim.x) {
+    const int r = i / (DH / 4), c4 = i % (DH / 4);
+    reinterpret_cast<float4*>(sK)[i] = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * D + D + c4 * 4);
+    reinterpret_cast<float4*>(sV)[i] = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * D + 2 * D + c4 * 4);
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)DH);
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    float q[DH], o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; d += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)t * 3 * D + d);
+      q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
+      o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
+    }
+    float mx = -INFINITY, l = 0.f;
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      float s[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        float acc = 0.f;
+        if (j < n) {
+          const float4* kr = reinterpret_cast<const float4*>(sK + (size_t)j * DH);
+#pragma unroll
+          for (int d4 = 0; d4 < DH / 4; ++d4) {
+            const float4 kk = kr[d4];
+            acc = fmaf(q[4 * d4], kk.x, acc); acc = fmaf(q[4 * d4 + 1], kk.y, acc);
+            acc = fmaf(q[4 * d4 + 2], kk.z, acc); acc = fmaf(q[4 * d4 + 3], kk.w, acc);
+          }
+        } else {
+          acc = -INFINITY;
+        }
+        s[u] = acc;
+      }
+      const float cm = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+      if (cm > mx) {
+        const float r = expf(mx - cm);  // exp(-inf) = 0 on the first chunk
+        l *= r;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) o[d] *= r;
+        mx = cm;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j >= n) continue;
+        const float pj = expf(s[u] - mx);
+        l += pj;
+        const float4* vr = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
+#pragma unroll
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
+          const float4 vv = vr[d4];
+          o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
+          o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+        }
+      }
+    }
+    const float inv = 1.0f / l;
+    const int64_t row = (int64_t)b * n + t;
+#pragma unroll
+    for (int d = 0; d < DH; d += 4)
+      store_operand4<PREC>(out_op, row, h * DH + d, D, make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv));
+  }
+}
+
+template <int PREC, int DH>
+static int launch_attention_t(const float* qkv, int batch, int n, int heads, void* out_op, cudaStream_t st) {
+  auto kern = attention_simt_kernel<PREC, DH>;
+  const size_t smem = (size_t)2 * n * DH * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const int threads = n >= 256 ? 256 : ((n + 31) / 32) * 32;
+  kern<<<batch * heads, threads, smem, st>>>(qkv, n, heads, out_op);
+  count_launch();
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int launch_attention(int prec, const float* qkv, int batch, int n, int heads, int dh, void* out_op, cudaStream_t st) {
+  PP_REQUIRE(dh == 32 || dh == 64, PP_ERR_UNSUPPORTED, "attention head width %d not built (32, 64)", dh);
+  PP_REQUIRE((size_t)2 * n * dh * 4 <= 200 * 1024, PP_ERR_UNSUPPORTED, "attention: %d tokens do not fit shared memory", n);
+  if (batch == 0) return PP_OK;
+  int rc = PP_OK;
+  if (dh == 32) { PP_DISPATCH_PREC(prec, (rc = launch_attention_t<PREC, 32>(qkv, batch, n, heads, out_op, st))); }
+  else          { PP_DISPATCH_PREC(prec, (rc = launch_attention_t<PREC, 64>(qkv, batch, n, heads, out_op, st))); }
+  return rc;
+}
+
+// ---- layout changes -----------------------------------------------------------------------
+// (B * hw, c) rows -> (B, c, hw): 32 x 32 shared-memory transpose tiles.
+__global__ void __launch_bounds__(256) rows_to_nchw_kernel(const float* __restrict__ rows, int hw, int c, float* nchw) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (p0 + r < hw && c0 + tx < c) tile[r][tx] = rows[((size_t)b * hw + p0 + r) * c + c0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < c && p0 + tx < hw) nchw[((size_t)b * c + c0 + r) * hw + p0 + tx] = tile[tx][r];
+}
+
+int launch_rows_to_nchw(const float* rows, int batch, int hw, int c, float* nchw, cudaStream_t st) {
+  if (batch == 0) return PP_OK;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
+  rows_to_nchw_kernel<<<grid, 256, 0, st>>>(rows, hw, c, nchw);
+  count_launch();
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(256) nchw_to_operand_kernel(const float* __restrict__ nchw, int hw, int c, void* rows_op) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < c && p0 + tx < hw) tile[r][tx] = nchw[((size_t)b * c + c0 + r) * hw + p0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (p0 + r < hw && c0 + tx < c) store_operand<PREC>(rows_op, (int64_t)b * hw + p0 + r, c0 + tx, c, tile[tx][r]);
+}
+
+int launch_nchw_to_operand(int prec, const float* nchw, int batch, int hw, int c, void* rows_op, cudaStream_t st) {
+  if (batch == 0) return PP_OK;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
+  PP_DISPATCH_PREC(prec, (nchw_to_operand_kernel<PREC><<<grid, 256, 0, st>>>(nchw, hw, c, rows_op)));
+  count_launch();
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+}  // namespace pp

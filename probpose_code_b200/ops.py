@@ -86,7 +86,8 @@ def to_operand(x: torch.Tensor, precision: int) -> torch.Tensor:
 def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precision: int, *,
          scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE, out_kind: int = _lib.OUT_F32,
-         out: Optional[torch.Tensor] = None, ldd: Optional[int] = None, plane: int = 0, up=None, tile_n: int = 0):
+         out: Optional[torch.Tensor] = None, ldd: Optional[int] = None, plane: int = 0, up=None, tile_n: int = 0,
+         res_mod: int = 0):
     """``pp_gemm``: D = epilogue(A . W^T).  ``a_op`` / ``w_op`` are operand buffers from
     :func:`to_operand`.  Returns the output tensor (fp32, or a uint8 operand buffer)."""
     dev = a_op.device
@@ -107,7 +108,7 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
             out = torch.empty((m // plane, n, plane), dtype=torch.float32, device=dev)
     hin, win, py, px = up if up is not None else (0, 0, 0, 0)
     args = _lib.GemmArgs(precision, m, n, k, a_op.data_ptr(), w_op.data_ptr(), _ptr(scale), _ptr(shift),
-                         _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n)
+                         _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n, res_mod)
     with torch.cuda.device(dev):
         check(lib().pp_gemm(C.byref(args), _stream()), "pp_gemm")
     return out

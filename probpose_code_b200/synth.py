@@ -23,7 +23,7 @@ def _tn(gen, shape, std):
     return t
 
 
-def make_state_dict(seed: int = 0, arch: dict = VIT_SMALL, head_std: float = 0.05, final_std: float = 0.25,
+def make_state_dict(seed: int = 0, arch: dict = VIT_SMALL, head_std: float = 0.05, final_std: float = 0.03,
                     branch_std: float = 0.02, tokens: int = 192, keypoints: int = 17,
                     deconv_channels=(256, 256)) -> dict:
     """ViT: trunc_normal(0.02) weights / pos_embed, LN affine slightly perturbed;
