@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py - persons/sec of the ProbPose top-down inference hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision P] [--batch B]
+
+One "step" = one pass of the whole path (uint8 crops -> ViT-S -> ProbMapHead -> fused
+sparsemax / flip-TTA / ProbMap decode -> (B, 17, 7) records) over one batch of B=64 synthetic
+256x192 crops per GPU with ``flip_test=True`` (the shipped config), BASELINE.json configs[1].
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+
+* ``value``   crops resident in HBM before the timed region, CUDA events, max over ranks.
+* ``e2e``     the same through the public plugin call ``TopdownPoseEstimator.test_step`` with
+              pinned HOST crops: H2D copy of the step's crops and D2H read of its records are
+              inside the timed region.
+* ``roofline``     the dominant kernel class (tensor-core GEMMs), per-launch average measured
+              with CUDA event pairs around every launch (``pp_engine_profile_*``).
+* ``decode_roofline`` the HBM-bound fused decode kernel, same method.
+* ``cpu_baseline`` the oracle (reference decode code restated + fp32 torch model) on the host
+              cores, bounded sample, rank 0 only.
+* ``--impl reference`` times that CPU path alone, same JSON contract.
+
+Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "persons_per_sec_256x192"
+UNIT = "persons/s"
+GFLOP_PER_PERSON_PASS = 13.4386  # ViT-S 8.9465 + heatmap 2.2413 + 4 branches 2.2508
+DECODE_BYTES_PER_PERSON = {True: 418268, False: 209372}  # section 8(d): 2 x 17*64*48*4 (+476 record) / single pass
+WORKLOAD = "ProbPose-small 256x192 batch=64/GPU flip_test=True random-init weights, ViT+head+decode end-to-end"
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    except Exception:  # noqa: BLE001
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None,
+                    sm_max_mhz=int(self.samples[0][1]) if self.samples and self.samples[0][1].isdigit() else None,
+                    reasons=sorted(reasons), samples=len(self.samples))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(sample: int, steps: int, warmup: int, flip: bool = True) -> dict:
+    from oracle import model_oracle
+    from probpose_code_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = model_oracle.ProbPoseRef().eval()
+    ref.load_state_dict(synth.make_state_dict(seed=0))
+    crops = synth.make_crops(sample, seed=100)
+    x = ref.preprocess(crops)
+    for _ in range(warmup):
+        ref.predict(x[: max(1, sample // 4)], flip_test=flip)
+    tm, model_s, decode_s = {}, 0.0, 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.predict(ref.preprocess(crops), flip_test=flip, timings=tm)
+        model_s += tm["model_s"]
+        decode_s += tm["decode_s"]
+    dt = time.perf_counter() - t0
+    return dict(value=sample * steps / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{steps} x {sample} crops of the same synthetic workload, flip_test={flip}; fp32 torch model on "
+                       f"{cores} threads ({model_s / dt:.0%} of time) + per-person scipy decode on 1 thread ({decode_s / dt:.0%})",
+                seconds=dt)
+
+
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return
+    sample = 8
+    r = cpu_reference(sample, args.steps, min(args.warmup, 1))
+    line = dict(metric=METRIC, value=r["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["seconds"] / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, note=f"each step is a bounded sample of {sample} crops of that workload on the host CPU"),
+                cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
+                e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp16x3", help="fp16x3 (parity mode, the headline) | fp16 | bf16 | fp32_simt")
+    ap.add_argument("--batch", type=int, default=64, help="crops per GPU per step")
+    ap.add_argument("--no-flip", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    flip = not args.no_flip
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: probpose_code_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import probpose_code_b200.mmpose_api as api
+    from probpose_code_b200 import synth
+
+    B = args.batch
+    model = api.MODELS.build(api.probpose_small_cfg(precision=args.precision, flip_test=flip))
+    model.load_state_dict(synth.make_state_dict(seed=0))
+    model.to(dev)
+    samples = api.make_data_samples(B)
+
+    # 16 rotating input batches (151 MB of uint8 crops at B=64) > the 126 MB L2
+    n_rot = 16
+    host = [synth.make_crops(B, seed=1000 * rank + i).pin_memory() for i in range(n_rot)]
+    resident = [h.to(dev) for h in host]
+    eng = model._fused_engine(B, dev)
+    rec = torch.empty((B, 17, 7), dtype=torch.float32, device=dev)
+    from probpose_code_b200.sharding import gather_records
+    fi = api.COCO_FLIP_INDICES
+
+    def step(i):
+        eng.infer(resident[i % n_rot], flip_test=flip, flip_indices=fi, out=rec)
+        if world > 1:  # the path's one exchange step: all-gather of the decoded records
+            gather_records(rec, world * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches = eng.last_launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+
+    # ---- e2e: public plugin API, host crops in, host records out, every step ----
+    def e2e_step(i):
+        out = model.test_step(dict(inputs=host[i % n_rot], data_samples=samples))
+        return out[0].pred_instances.keypoints  # numpy on the host (the D2H read happened inside)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(3 + i)
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)  # host packing counts too
+
+    # ---- per-kernel-class device times (event pair around every launch) ----
+    prof_steps = 3
+    eng.profile_begin()
+    for i in range(prof_steps):
+        eng.infer(resident[i % n_rot], flip_test=flip, flip_indices=fi, out=rec)
+    prof = eng.profile_end()
+
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peaks = load_peaks()
+        passes = 2 if flip else 1
+        persons = world * B * args.steps
+        gemm = prof["gemm"]
+        gemm_tf = prof["gemm_flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+        dec = prof["decode"]
+        dec_bytes = DECODE_BYTES_PER_PERSON[flip] * B
+        dec_gbs = dec_bytes * dec["launches"] / (dec["ms"] * 1e-3) / 1e9 if dec["ms"] > 0 else 0.0
+        step_ms_prof = sum(prof[k]["ms"] for k in ("gemm", "attention", "decode", "other")) / prof_steps
+        line = dict(
+            metric=METRIC, value=persons / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype={"fp16x3": "fp16x3 (fp16 hi+lo split operands, 3 tcgen05 MMAs per product, fp32 accumulate)",
+                   "fp16": "fp16 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)", "fp32_simt": "f32"}[args.precision],
+            data="synthetic",
+            config=dict(workload=WORKLOAD if (B == 64 and flip) else f"ProbPose-small 256x192 batch={B}/GPU flip_test={flip}",
+                        batch_per_gpu=B, flip_test=flip, precision=args.precision, parallelism=f"dp{world}",
+                        l2=f"{n_rot} rotating input batches ({n_rot * B * 147456 / 1e6:.0f} MB uint8) > 126 MB L2; "
+                           "activations per step ~1 GB"),
+            clocks=clocks,
+            e2e=dict(value=persons / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * 3 * 256 * 192,
+                     d2h_bytes_per_step=B * 17 * 7 * 4, api="TopdownPoseEstimator.test_step(pinned uint8 crops) -> host numpy"),
+            gpu_launches=int(launches) * args.steps,
+            roofline=dict(bound="tensor", kernel="gemm_tc_kernel (all tcgen05 GEMM launches of a step)", achieved=gemm_tf,
+                          peak=peaks["tf_sustained"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_sustained"], traffic=None,
+                          peak_source=peaks["source"] + " bf16 sustained",
+                          launches_per_step=gemm["launches"] // prof_steps, share_of_step=gemm["ms"] / prof_steps / step_ms_prof,
+                          whole_step_tflops=GFLOP_PER_PERSON_PASS * passes * B / (ms / args.steps * 1e-3) / 1e3),
+            decode_roofline=dict(bound="hbm", kernel="decode_kernel", achieved=dec_gbs, peak=peaks["hbm"], unit="GB/s",
+                                 frac=dec_gbs / peaks["hbm"], traffic=None, bytes_per_launch=dec_bytes,
+                                 us_per_launch=dec["ms"] / max(dec["launches"], 1) * 1e3,
+                                 share_of_step=dec["ms"] / prof_steps / step_ms_prof),
+            kernel_ms_per_step={k: prof[k]["ms"] / prof_steps for k in ("gemm", "attention", "decode", "other")},
+        )
+        if not args.no_cpu_baseline:
+            r = cpu_reference(32, 1, 1, flip)
+            line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

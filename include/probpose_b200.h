@@ -192,6 +192,21 @@ PP_API int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const floa
 /* Number of kernels the last pp_engine_* call launched (bench.py's gpu_launches). */
 PP_API int64_t pp_engine_last_launch_count(const pp_engine* e);
 
+/* Per-kernel-class device timing (bench.py's roofline numbers).  Between _begin and _end
+ * every kernel a pp_engine_* call launches is bracketed by a CUDA event pair on the caller's
+ * stream; _end synchronises that stream and sums the elapsed times per class.  gemm_flops is
+ * the algorithmic 2*m*n*k of the GEMM launches (the FP16X3 triple issue is NOT counted). */
+typedef enum pp_kernel_class {
+  PP_KC_GEMM = 0, PP_KC_ATTENTION = 1, PP_KC_DECODE = 2, PP_KC_OTHER = 3, PP_KC_COUNT = 4
+} pp_kernel_class;
+typedef struct pp_profile {
+  double ms[PP_KC_COUNT];
+  int64_t launches[PP_KC_COUNT];
+  double gemm_flops;
+} pp_profile;
+PP_API int pp_engine_profile_begin(pp_engine* e);
+PP_API int pp_engine_profile_end(pp_engine* e, pp_profile* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

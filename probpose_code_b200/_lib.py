@@ -22,7 +22,9 @@ EXPORTS = [
     "pp_last_error", "pp_version", "pp_decode", "pp_gemm", "pp_operand_bytes", "pp_operand_from_f32",
     "pp_engine_workspace_bytes", "pp_engine_create", "pp_engine_destroy", "pp_engine_load", "pp_engine_finalize",
     "pp_engine_backbone", "pp_engine_head", "pp_engine_infer", "pp_engine_last_launch_count",
+    "pp_engine_profile_begin", "pp_engine_profile_end",
 ]
+KERNEL_CLASSES = ("gemm", "attention", "decode", "other")
 
 
 class DecodeCfg(C.Structure):
@@ -45,6 +47,10 @@ class EngineCfg(C.Structure):
                 ("heads", C.c_int32), ("ffn_dim", C.c_int32), ("num_keypoints", C.c_int32),
                 ("deconv_channels", C.c_int32), ("ln_eps", C.c_float), ("bn_eps", C.c_float),
                 ("temperature", C.c_float), ("normalize", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("launches", C.c_int64 * 4), ("gemm_flops", C.c_double)]
 
 
 class PPError(RuntimeError):
@@ -71,7 +77,7 @@ def lib() -> C.CDLL:
     l.pp_decode.argtypes = [C.POINTER(DecodeCfg), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p,
                             C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     l.pp_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
-    if hasattr(l, "pp_engine_create"):
+    if True:
         l.pp_engine_workspace_bytes.restype = C.c_size_t
         l.pp_engine_workspace_bytes.argtypes = [C.POINTER(EngineCfg)]
         l.pp_engine_create.argtypes = [C.POINTER(EngineCfg), C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -85,6 +91,8 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         l.pp_engine_last_launch_count.restype = C.c_int64
         l.pp_engine_last_launch_count.argtypes = [C.c_void_p]
+        l.pp_engine_profile_begin.argtypes = [C.c_void_p]
+        l.pp_engine_profile_end.argtypes = [C.c_void_p, C.POINTER(Profile), C.c_void_p]
     _lib = l
     return l
 

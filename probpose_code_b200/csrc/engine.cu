@@ -55,6 +55,12 @@ struct pp_engine {
   std::unordered_map<std::string, int> index;
   bool backbone_ready = false, head_ready = false;
   int64_t last_launches = 0;
+  // optional per-class event timing (pp_engine_profile_*)
+  bool profiling = false;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_gemm_flops = 0;
 
   // packed weights (byte offsets)
   size_t w_patch;
@@ -233,6 +239,31 @@ static pp_gemm_args gemm_args(const pp_engine* e, int64_t m, int n, int k, const
   return g;
 }
 
+// Runs one launcher; when profiling, brackets it with an event pair on the stream.
+template <typename F>
+static int timed(pp_engine* e, int cls, cudaStream_t st, F&& launch) {
+  if (!e->profiling) return launch();
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; ++i) {
+    if (e->event_pool.empty()) {
+      PP_CHECK_CUDA(cudaEventCreate(&ev[i]));
+    } else {
+      ev[i] = e->event_pool.back();
+      e->event_pool.pop_back();
+    }
+  }
+  PP_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  const int rc = launch();
+  PP_CHECK_CUDA(cudaEventRecord(ev[1], st));
+  e->spans.push_back({cls, ev[0], ev[1]});
+  return rc;
+}
+
+static int gemm(pp_engine* e, const pp_gemm_args& g, cudaStream_t st) {
+  if (e->profiling) e->prof_gemm_flops += 2.0 * g.m * g.n * g.k;
+  return timed(e, PP_KC_GEMM, st, [&] { return gemm_dispatch(g, st); });
+}
+
 #define PP_TRY(expr)            \
   do {                          \
     const int _rc = (expr);     \
@@ -253,39 +284,39 @@ static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int ba
   pp_.img_h = e->cfg.img_h; pp_.img_w = e->cfg.img_w; pp_.patch = e->cfg.patch; pp_.pad = e->cfg.patch_pad;
   pp_.gh = e->gh; pp_.gw = e->gw;
   for (int c = 0; c < 3; ++c) { pp_.mean[c] = e->cfg.mean[c]; pp_.inv_std[c] = 1.0f / e->cfg.std[c]; }
-  PP_TRY(launch_patchify(prec, pp_, e->at<>(e->a_op), st));
+  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_patchify(prec, pp_, e->at<>(e->a_op), st); }));
   {
     pp_gemm_args g = gemm_args(e, M, D, e->PK, e->at<>(e->a_op), e->at<>(e->w_patch));
     g.shift = e->P("backbone.patch_embed.projection.bias");
     g.residual = e->P("backbone.pos_embed"); g.res_mod = e->tokens;
     g.d = e->at<>(e->x);
-    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(gemm(e, g, st));
   }
   float* x = e->at<float>(e->x);
   for (int l = 0; l < e->depth; ++l) {
     const std::string p = "backbone.layers." + std::to_string(l) + ".";
     const pp_engine::Layer& L = e->layers[l];
-    PP_TRY(launch_layernorm(prec, x, e->P(p + "ln1.weight"), e->P(p + "ln1.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
-                            nullptr, st));
+    PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P(p + "ln1.weight"), e->P(p + "ln1.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
+                            nullptr, st); }));
     pp_gemm_args g = gemm_args(e, M, 3 * D, D, e->at<>(e->a_op), e->at<>(L.wqkv));
     g.shift = e->P(p + "attn.qkv.bias"); g.d = e->at<>(e->qkv);
-    PP_TRY(gemm_dispatch(g, st));
-    PP_TRY(launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st));
+    PP_TRY(gemm(e, g, st));
+    PP_TRY(timed(e, PP_KC_ATTENTION, st, [&] { return launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st); }));
     g = gemm_args(e, M, D, D, e->at<>(e->a_op), e->at<>(L.wproj));
     g.shift = e->P(p + "attn.proj.bias"); g.residual = x; g.d = x;
-    PP_TRY(gemm_dispatch(g, st));
-    PP_TRY(launch_layernorm(prec, x, e->P(p + "ln2.weight"), e->P(p + "ln2.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
-                            nullptr, st));
+    PP_TRY(gemm(e, g, st));
+    PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P(p + "ln2.weight"), e->P(p + "ln2.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
+                            nullptr, st); }));
     g = gemm_args(e, M, FF, D, e->at<>(e->a_op), e->at<>(L.wfc1));
     g.shift = e->P(p + "ffn.layers.0.0.bias"); g.act = PP_ACT_GELU; g.out_kind = PP_OUT_OPERAND; g.ldd = FF;
     g.d = e->at<>(e->h_op);
-    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(gemm(e, g, st));
     g = gemm_args(e, M, D, FF, e->at<>(e->h_op), e->at<>(L.wfc2));
     g.shift = e->P(p + "ffn.layers.1.bias"); g.residual = x; g.d = x;
-    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(gemm(e, g, st));
   }
-  PP_TRY(launch_layernorm(prec, x, e->P("backbone.ln1.weight"), e->P("backbone.ln1.bias"), e->cfg.ln_eps, M, D,
-                          e->at<>(e->feat_op), want_f32 ? e->at<float>(e->feat_f32) : nullptr, st));
+  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P("backbone.ln1.weight"), e->P("backbone.ln1.bias"), e->cfg.ln_eps, M, D,
+                          e->at<>(e->feat_op), want_f32 ? e->at<float>(e->feat_f32) : nullptr, st); }));
   return PP_OK;
 }
 
@@ -308,47 +339,47 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
         deconv_tap(py, t >> 1, &gp.dy[t], &kk);
         deconv_tap(px, t & 1, &gp.dx[t], &kk);
       }
-      PP_TRY(launch_gather_taps(prec, gp, src, e->at<>(e->g_op), st));
+      PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_gather_taps(prec, gp, src, e->at<>(e->g_op), st); }));
       pp_gemm_args g = gemm_args(e, rows, DC, 4 * cin, e->at<>(e->g_op), e->at<>(e->w_dc[i][ph]));
       g.scale = e->at<float>(e->dc_scale[i]); g.shift = e->at<float>(e->dc_shift[i]); g.act = PP_ACT_RELU;
       g.out_kind = PP_OUT_OPERAND; g.ldd = DC; g.d = dst;
       g.up_hin = h; g.up_win = w; g.up_py = py; g.up_px = px;
-      PP_TRY(gemm_dispatch(g, st));
+      PP_TRY(gemm(e, g, st));
     }
   }
   {
     pp_gemm_args g = gemm_args(e, 16 * M, K, DC, e->at<>(e->d2_op), e->at<>(e->w_final));
     g.shift = e->P("head.final_layer.bias"); g.out_kind = PP_OUT_PLANES; g.plane = 16 * e->tokens; g.d = logits;
-    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(gemm(e, g, st));
   }
   // --- four scalar branches; the first conv of all four shares its input -> one GEMM, N = 4 D ---
   GatherParams g3 = {};
   g3.ntaps = 9;
   for (int t = 0; t < 9; ++t) { g3.dy[t] = t / 3 - 1; g3.dx[t] = t % 3 - 1; }
   g3.batch = n_img; g3.h = e->gh; g3.w = e->gw; g3.c = D; g3.src_c = D; g3.c_off = 0;
-  PP_TRY(launch_gather_taps(prec, g3, e->at<>(e->feat_op), e->at<>(e->g_op), st));
+  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_gather_taps(prec, g3, e->at<>(e->feat_op), e->at<>(e->g_op), st); }));
   {
     pp_gemm_args g = gemm_args(e, M, 4 * D, 9 * D, e->at<>(e->g_op), e->at<>(e->w_c1));
     g.scale = e->at<float>(e->c_scale[0]); g.shift = e->at<float>(e->c_shift[0]); g.d = e->at<>(e->c_f32);
-    PP_TRY(gemm_dispatch(g, st));
+    PP_TRY(gemm(e, g, st));
   }
   int h = e->gh, w = e->gw;
   const int pool[3][2] = {{4, 3}, {2, 2}, {2, 2}};  // probmap_head.py:264
   for (int j = 1; j < 3; ++j) {
-    PP_TRY(launch_pool_relu(prec, e->at<float>(e->c_f32), n_img, h, w, 4 * D, pool[j - 1][0], pool[j - 1][1],
-                            e->at<>(e->pool_op), st));
+    PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_pool_relu(prec, e->at<float>(e->c_f32), n_img, h, w, 4 * D, pool[j - 1][0], pool[j - 1][1],
+                            e->at<>(e->pool_op), st); }));
     h /= pool[j - 1][0]; w /= pool[j - 1][1];
     const int64_t rows = (int64_t)n_img * h * w;
     for (int br = 0; br < 4; ++br) {
       g3.h = h; g3.w = w; g3.src_c = 4 * D; g3.c_off = br * D;
-      PP_TRY(launch_gather_taps(prec, g3, e->at<>(e->pool_op), e->at<>(e->g_op), st));
+      PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_gather_taps(prec, g3, e->at<>(e->pool_op), e->at<>(e->g_op), st); }));
       pp_gemm_args g = gemm_args(e, rows, D, 9 * D, e->at<>(e->g_op), e->at<>(j == 1 ? e->w_c2[br] : e->w_c3[br]));
       g.scale = e->at<float>(e->c_scale[j]) + br * D; g.shift = e->at<float>(e->c_shift[j]) + br * D;
       g.ldd = 4 * D; g.d = e->at<float>(e->c_f32) + br * D;
-      PP_TRY(gemm_dispatch(g, st));
+      PP_TRY(gemm(e, g, st));
     }
   }
-  PP_TRY(launch_branch_tail(e->at<float>(e->c_f32), n_img, D, K, e->at<float>(e->tail_w), e->at<float>(e->tail_b), scalars, st));
+  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_branch_tail(e->at<float>(e->c_f32), n_img, D, K, e->at<float>(e->tail_w), e->at<float>(e->tail_b), scalars, st); }));
   return PP_OK;
 }
 
@@ -391,7 +422,12 @@ extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_
   return PP_OK;
 }
 
-extern "C" void pp_engine_destroy(pp_engine* e) { delete e; }
+extern "C" void pp_engine_destroy(pp_engine* e) {
+  if (!e) return;
+  for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (auto ev : e->event_pool) cudaEventDestroy(ev);
+  delete e;
+}
 
 extern "C" int pp_engine_load(pp_engine* e, const char* name, const float* data, int64_t numel, void* stream) {
   PP_REQUIRE(e && name && data, PP_ERR_INVALID, "pp_engine_load: NULL argument");
@@ -523,11 +559,41 @@ extern "C" int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const 
     dc.num_keypoints = e->K; dc.height = 4 * e->gh; dc.width = 4 * e->gw; dc.input_is_logits = 1;
     dc.temperature = e->cfg.temperature; dc.normalize = e->cfg.normalize; dc.error_divisor = 0.f;
     const size_t map_stride = (size_t)batch * e->K * 16 * e->tokens, sc_stride = (size_t)batch * 4 * e->K;
-    PP_TRY(pp_decode(&dc, logits, flip_test ? logits + map_stride : nullptr, flip_indices, scal,
-                     flip_test ? scal + sc_stride : nullptr, batch, records, merged_out, stream));
+    PP_TRY(timed(e, PP_KC_DECODE, st, [&] {
+      return pp_decode(&dc, logits, flip_test ? logits + map_stride : nullptr, flip_indices, scal,
+                       flip_test ? scal + sc_stride : nullptr, batch, records, merged_out, stream);
+    }));
   }
   e->last_launches = g_launch_count - before;
   return PP_OK;
 }
 
 extern "C" int64_t pp_engine_last_launch_count(const pp_engine* e) { return e ? e->last_launches : 0; }
+
+extern "C" int pp_engine_profile_begin(pp_engine* e) {
+  PP_REQUIRE(e != nullptr, PP_ERR_INVALID, "pp_engine_profile_begin: engine is NULL");
+  for (auto& s : e->spans) { e->event_pool.push_back(s.a); e->event_pool.push_back(s.b); }
+  e->spans.clear();
+  e->prof_gemm_flops = 0;
+  e->profiling = true;
+  return PP_OK;
+}
+
+extern "C" int pp_engine_profile_end(pp_engine* e, pp_profile* out, void* stream) {
+  PP_REQUIRE(e && out, PP_ERR_INVALID, "pp_engine_profile_end: NULL argument");
+  PP_REQUIRE(e->profiling, PP_ERR_STATE, "pp_engine_profile_end without pp_engine_profile_begin");
+  e->profiling = false;
+  PP_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int c = 0; c < PP_KC_COUNT; ++c) { out->ms[c] = 0; out->launches[c] = 0; }
+  for (auto& s : e->spans) {
+    float ms = 0.f;
+    PP_CHECK_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+    out->ms[s.cls] += ms;
+    out->launches[s.cls] += 1;
+    e->event_pool.push_back(s.a);
+    e->event_pool.push_back(s.b);
+  }
+  e->spans.clear();
+  out->gemm_flops = e->prof_gemm_flops;
+  return PP_OK;
+}

@@ -142,3 +142,16 @@ class Engine:
     @property
     def last_launch_count(self) -> int:
         return int(lib().pp_engine_last_launch_count(self._h))
+
+    def profile_begin(self) -> None:
+        check(lib().pp_engine_profile_begin(self._h), "pp_engine_profile_begin")
+
+    def profile_end(self) -> dict:
+        """Per-kernel-class device time (ms), launch counts and GEMM algorithmic FLOPs since
+        :meth:`profile_begin` (synchronises the current stream)."""
+        prof = _lib.Profile()
+        with torch.cuda.device(self.device):
+            check(lib().pp_engine_profile_end(self._h, C.byref(prof), _stream()), "pp_engine_profile_end")
+        out = {name: dict(ms=prof.ms[i], launches=int(prof.launches[i])) for i, name in enumerate(_lib.KERNEL_CLASSES)}
+        out["gemm_flops"] = prof.gemm_flops
+        return out

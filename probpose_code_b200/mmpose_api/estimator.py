@@ -1,0 +1,214 @@
+"""``TopdownPoseEstimator`` + ``PoseDataPreprocessor`` for the predict path
+(mmpose/models/pose_estimators/{base,topdown}.py, models/data_preprocessors/data_preprocessor.py).
+
+When backbone and head are this package's ``VisionTransformer`` and ``ProbMapHead`` the whole
+``predict`` is ONE engine call (``pp_engine_infer``): uint8 crops in, (B, K, 7) records out, with
+preprocessing, both flip passes, sparsemax, TTA merge and decode on the device.  Any other
+combination falls back to the reference's generic module-by-module flow (still CUDA modules -
+there is no CPU path)."""
+from __future__ import annotations
+
+from itertools import zip_longest
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from ._engine_cache import EngineCache
+from .backbone import VisionTransformer
+from .head import ProbMapHead
+from .registry import MODELS, register
+from .structures import PixelData
+
+
+@register(MODELS, ["PoseDataPreprocessor"])
+class PoseDataPreprocessor(nn.Module):
+    """BGR->RGB, float, ``(x - mean) / std``, stack (data_preprocessor.py:79-104 + mmengine
+    ``ImgDataPreprocessor``).  Used on the generic path; the fused path hands the uint8 crops to
+    the engine, which applies the same arithmetic inside the patch-extraction kernel."""
+
+    def __init__(self, mean: Sequence[float] = None, std: Sequence[float] = None, pad_size_divisor: int = 1,
+                 pad_value=0, bgr_to_rgb: bool = False, rgb_to_bgr: bool = False, non_blocking: bool = False,
+                 batch_augments=None):
+        super().__init__()
+        assert not (bgr_to_rgb and rgb_to_bgr), "`bgr2rgb` and `rgb2bgr` cannot be set to True at the same time"
+        assert (mean is None) == (std is None), "mean and std should be both None or tuple"
+        self.channel_conversion = bgr_to_rgb or rgb_to_bgr
+        self.mean_std = None if mean is None else (tuple(mean), tuple(std))
+        if mean is not None:
+            self.register_buffer("mean", torch.tensor(mean).view(-1, 1, 1), False)
+            self.register_buffer("std", torch.tensor(std).view(-1, 1, 1), False)
+
+    @staticmethod
+    def stack(inputs) -> torch.Tensor:
+        return torch.stack(list(inputs)) if not isinstance(inputs, torch.Tensor) else inputs
+
+    def forward(self, data: dict, training: bool = False) -> dict:
+        x = self.stack(data["inputs"]).to(self.mean.device if self.mean_std else None)
+        if self.channel_conversion:
+            x = x[:, [2, 1, 0]]
+        x = x.float()
+        if self.mean_std:
+            x = (x - self.mean) / self.std
+        return {"inputs": x, "data_samples": data.get("data_samples")}
+
+
+@register(MODELS, ["TopdownPoseEstimator"])
+class TopdownPoseEstimator(nn.Module):
+    _version = 2
+
+    def __init__(self, backbone: dict, neck: Optional[dict] = None, head: Optional[dict] = None,
+                 train_cfg: Optional[dict] = None, test_cfg: Optional[dict] = None,
+                 data_preprocessor: Optional[dict] = None, init_cfg=None, metainfo: Optional[dict] = None,
+                 freeze_backbone: bool = False, precision: str = None):
+        super().__init__()
+        self.metainfo = metainfo
+        self.train_cfg = train_cfg if train_cfg else {}
+        self.test_cfg = test_cfg if test_cfg else {}
+        if precision is not None:
+            backbone = dict(backbone, precision=precision)
+            head = dict(head, precision=precision) if head is not None else None
+        self.data_preprocessor = MODELS.build(data_preprocessor or dict(type="PoseDataPreprocessor"))
+        self.backbone = MODELS.build(backbone)
+        if neck is not None:
+            self.neck = MODELS.build(neck)
+        if head is not None:
+            self.head = MODELS.build(head)
+            self.head.test_cfg = self.test_cfg.copy()
+        self._fused = None
+        self.eval()
+
+    with_neck = property(lambda self: hasattr(self, "neck") and self.neck is not None)
+    with_head = property(lambda self: hasattr(self, "head") and self.head is not None)
+
+    # ---- fused engine -----------------------------------------------------------------
+    def _fusable(self) -> bool:
+        return (isinstance(self.backbone, VisionTransformer) and self.with_head and isinstance(self.head, ProbMapHead)
+                and not self.with_neck and self.head.decoder is not None
+                and self.backbone._cache.precision == self.head._cache.precision)
+
+    def _fused_engine(self, batch: int, device):
+        if self._fused is None:
+            kw = dict(self.backbone._cache.kwargs)
+            hk = self.head._cache.kwargs
+            kw.update(num_keypoints=hk["num_keypoints"], deconv_channels=hk["deconv_channels"],
+                      temperature=hk["temperature"], normalize=hk["normalize"])
+            pre = self.data_preprocessor
+            if getattr(pre, "mean_std", None):
+                kw.update(mean=pre.mean_std[0], std=pre.mean_std[1])
+            self._fused = EngineCache(kw, self.backbone._cache.precision)
+        tensors = dict(self.backbone.engine_tensors())
+        tensors.update(self.head.engine_tensors())
+        return self._fused.get(tensors, batch, device)
+
+    def _device(self):
+        return self.backbone.pos_embed.device
+
+    # ---- mmengine BaseModel surface -----------------------------------------------------
+    @torch.no_grad()
+    def test_step(self, data: dict) -> list:
+        """``BaseModel.test_step``: ``data = dict(inputs=[uint8 BGR (3,H,W)...], data_samples=[...])``."""
+        inputs = PoseDataPreprocessor.stack(data["inputs"])
+        pre = self.data_preprocessor
+        if (self._fusable() and inputs.dtype == torch.uint8 and getattr(pre, "channel_conversion", False)
+                and getattr(pre, "mean_std", None)):
+            return self._predict_fused(inputs.to(self._device(), non_blocking=True).contiguous(), data["data_samples"])
+        data = pre(data, False)
+        return self.forward(data["inputs"], data["data_samples"], mode="predict")
+
+    def forward(self, inputs: torch.Tensor, data_samples=None, mode: str = "tensor"):
+        """pose_estimators/base.py:123-168."""
+        if isinstance(inputs, list):
+            inputs = torch.stack(inputs)
+        if mode == "loss":
+            return self.loss(inputs, data_samples)
+        elif mode == "predict":
+            if self.metainfo is not None:
+                for data_sample in data_samples:
+                    data_sample.set_metainfo(self.metainfo)
+            return self.predict(inputs, data_samples)
+        elif mode == "tensor":
+            return self._forward(inputs)
+        raise RuntimeError(f'Invalid mode "{mode}". ' "Only supports loss, predict and tensor mode.")
+
+    def loss(self, inputs, data_samples):
+        raise NotImplementedError("training is out of scope of the B200 inference path")
+
+    def extract_feat(self, inputs: torch.Tensor):
+        x = self.backbone(inputs)
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+    def _forward(self, inputs: torch.Tensor, data_samples=None):
+        x = self.extract_feat(inputs)
+        if self.with_head:
+            x = self.head.forward(x)
+        return x
+
+    @torch.no_grad()
+    def predict(self, inputs: torch.Tensor, data_samples: list) -> list:
+        """topdown.py:86-126."""
+        assert self.with_head, "The model must have head to perform prediction."
+        if self._fusable():
+            return self._predict_fused(inputs.float().contiguous(), data_samples)
+        if self.test_cfg.get("flip_test", False):
+            feats = [self.extract_feat(inputs), self.extract_feat(inputs.flip(-1))]
+        else:
+            feats = self.extract_feat(inputs)
+        preds = self.head.predict(feats, data_samples, test_cfg=self.test_cfg)
+        if isinstance(preds, tuple):
+            batch_pred_instances, batch_pred_fields = preds
+        else:
+            batch_pred_instances, batch_pred_fields = preds, None
+        return self.add_pred_to_datasample(batch_pred_instances, batch_pred_fields, data_samples)
+
+    def _predict_fused(self, inputs: torch.Tensor, data_samples: list) -> list:
+        """One ``pp_engine_infer`` call for the batch (uint8 BGR or normalised fp32 crops)."""
+        cfg = self.test_cfg
+        self.head.check_test_cfg(cfg)
+        flip = bool(cfg.get("flip_test", False))
+        want_hm = bool(cfg.get("output_heatmaps", False))
+        flip_indices = data_samples[0].metainfo["flip_indices"] if flip else None
+        eng = self._fused_engine(inputs.shape[0], inputs.device)
+        out = eng.infer(inputs, flip_test=flip, flip_indices=flip_indices, return_heatmaps=want_hm)
+        records, heatmaps = out if want_hm else (out, None)
+        fields = [PixelData(heatmaps=hm) for hm in heatmaps] if want_hm else None
+        return self.add_pred_to_datasample(self.head.pack_records(records), fields, data_samples)
+
+    def add_pred_to_datasample(self, batch_pred_instances: list, batch_pred_fields: Optional[list],
+                               batch_data_samples: list) -> list:
+        """topdown.py:128-194: input space -> image space, copy the bbox fields."""
+        assert len(batch_pred_instances) == len(batch_data_samples)
+        if batch_pred_fields is None:
+            batch_pred_fields = []
+        output_keypoint_indices = self.test_cfg.get("output_keypoint_indices", None)
+        for pred_instances, pred_fields, data_sample in zip_longest(batch_pred_instances, batch_pred_fields,
+                                                                    batch_data_samples):
+            if pred_instances is None:
+                continue
+            gt_instances = data_sample.gt_instances
+            input_center = data_sample.metainfo["input_center"]
+            input_scale = data_sample.metainfo["input_scale"]
+            input_size = data_sample.metainfo["input_size"]
+            pred_instances.keypoints[..., :2] = (pred_instances.keypoints[..., :2] / input_size * input_scale
+                                                 + input_center - 0.5 * input_scale)
+            if "keypoints_visible" not in pred_instances:
+                pred_instances.keypoints_visible = pred_instances.keypoint_scores
+            if output_keypoint_indices is not None:
+                num_keypoints = pred_instances.keypoints.shape[1]
+                for key, value in pred_instances.all_items():
+                    if key.startswith("keypoint"):
+                        pred_instances.set_field(value[:, output_keypoint_indices], key)
+            pred_instances.bboxes = gt_instances.bboxes
+            pred_instances.bbox_scores = gt_instances.bbox_scores
+            data_sample.pred_instances = pred_instances
+            if pred_fields is not None:
+                if output_keypoint_indices is not None:
+                    for key, value in pred_fields.all_items():
+                        if value.shape[0] != num_keypoints:
+                            continue
+                        pred_fields.set_field(value[output_keypoint_indices], key)
+                data_sample.pred_fields = pred_fields
+        return batch_data_samples

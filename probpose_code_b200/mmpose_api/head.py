@@ -1,0 +1,213 @@
+"""``ProbMapHead`` with the reference's constructor, attribute names and ``state_dict`` layout
+(mmpose/models/heads/hybrid_heads/probmap_head.py), inference side only.  ``forward`` /
+``predict`` run on the sm_100a engine + fused decode kernel; the ``nn.Module`` children exist to
+hold the weights under the reference's names (``deconv_layers.{0,1,3,4}``, ``final_layer``,
+``{probability,visibility,oks,error}_layers.{0,1,4,5,8,9,12}``)."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from ._engine_cache import EngineCache
+from .registry import KEYPOINT_CODECS, MODELS, register
+from .structures import InstanceData, PixelData
+
+
+class BaseHead(nn.Module):
+    """mmpose/models/heads/base_head.py: ``decode`` dispatches to the codec."""
+
+    decoder = None
+
+    def forward(self, feats):
+        raise NotImplementedError
+
+    def predict(self, feats, batch_data_samples, test_cfg={}):
+        raise NotImplementedError
+
+    def loss(self, feats, batch_data_samples, train_cfg={}):
+        raise NotImplementedError
+
+    def decode(self, batch_outputs) -> List[InstanceData]:
+        """base_head.py:33-86.  The GPU codec always supports batch decoding; a foreign codec
+        without it is driven per instance on host copies exactly like the reference."""
+        args = batch_outputs if isinstance(batch_outputs, tuple) else (batch_outputs,)
+        if self.decoder is None:
+            raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__}. "
+                               "Please set the decoder configs in the init parameters to "
+                               "enable head methods `head.predict()` and `head.decode()`")
+        if self.decoder.support_batch_decoding:
+            batch_keypoints, batch_scores = self.decoder.batch_decode(*args)
+        else:
+            batch_keypoints, batch_scores = [], []
+            for outputs in zip(*[a.detach().cpu().numpy() for a in args]):
+                k, s = self.decoder.decode(*outputs)
+                batch_keypoints.append(k)
+                batch_scores.append(s)
+        return [InstanceData(keypoints=k, keypoint_scores=s) for k, s in zip(batch_keypoints, batch_scores)]
+
+
+def _scalar_branch(cin: int, cout: int, last: nn.Module) -> nn.Sequential:
+    mods = []
+    for ks in ((4, 3), (2, 2), (2, 2)):  # probmap_head.py:264: Conv -> BN -> MaxPool -> ReLU
+        mods += [nn.Conv2d(cin, cin, 3, 1, 1), nn.BatchNorm2d(cin), nn.MaxPool2d(ks, ks), nn.ReLU(inplace=True)]
+    mods += [nn.Conv2d(cin, cout, 1, 1, 0), last]
+    return nn.Sequential(*mods)
+
+
+@register(MODELS, ["ProbMapHead"])
+class ProbMapHead(BaseHead):
+    _version = 2
+
+    def __init__(self, in_channels: Union[int, Sequence[int]], out_channels: int,
+                 deconv_out_channels=(256, 256, 256), deconv_kernel_sizes=(4, 4, 4), conv_out_channels=None,
+                 conv_kernel_sizes=None, final_layer_dict: dict = dict(kernel_size=1), keypoint_loss=None,
+                 probability_loss=None, visibility_loss=None, oks_loss=None, error_loss=None, normalize: float = None,
+                 detach_probability: bool = True, detach_visibility: bool = True, learn_heatmaps_from_zeros: bool = False,
+                 freeze_heatmaps: bool = False, freeze_probability: bool = False, freeze_visibility: bool = False,
+                 freeze_oks: bool = False, freeze_error: bool = False,
+                 decoder=dict(type="UDPHeatmap", input_size=(192, 256), heatmap_size=(48, 64), sigma=2), init_cfg=None,
+                 precision: str = None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.temperature = 0.5  # probmap_head.py:135
+        self.normalize = normalize
+        self.freeze_oks, self.freeze_error = freeze_oks, freeze_error
+        self.test_cfg = {}
+        # the five loss configs are accepted and ignored: training is out of scope here
+        self.decoder = KEYPOINT_CODECS.build(decoder) if decoder is not None else None
+
+        if deconv_out_channels:
+            if deconv_kernel_sizes is None or len(deconv_out_channels) != len(deconv_kernel_sizes):
+                raise ValueError('"deconv_out_channels" and "deconv_kernel_sizes" should '
+                                 "be integer sequences with the same length. Got "
+                                 f"mismatched lengths {deconv_out_channels} and {deconv_kernel_sizes}")
+        unsupported = []
+        if not isinstance(in_channels, int): unsupported.append("multi-level in_channels")
+        if not deconv_out_channels or len(deconv_out_channels) != 2 or len(set(deconv_out_channels)) != 1:
+            unsupported.append(f"deconv_out_channels={deconv_out_channels} (two equal deconv layers)")
+        elif tuple(deconv_kernel_sizes) != (4, 4): unsupported.append(f"deconv_kernel_sizes={deconv_kernel_sizes} ((4, 4))")
+        if conv_out_channels: unsupported.append("conv_out_channels")
+        if final_layer_dict is None or dict(final_layer_dict).get("kernel_size", 1) != 1: unsupported.append("final layer != 1x1 conv")
+        if normalize is None: unsupported.append("normalize=None (the sparsemax-normalised head only)")
+        if unsupported:
+            raise NotImplementedError("probpose_code_b200 ProbMapHead covers the shipped ProbPose configuration only; "
+                                      "unsupported: " + ", ".join(unsupported))
+        layers, c = [], in_channels
+        for co in deconv_out_channels:  # probmap_head.py:441-470: k4 s2 p1 output_padding 0, no bias
+            layers += [nn.ConvTranspose2d(c, co, 4, 2, 1, 0, bias=False), nn.BatchNorm2d(co), nn.ReLU(inplace=True)]
+            c = co
+        self.deconv_layers = nn.Sequential(*layers)
+        self.conv_layers = nn.Identity()
+        self.final_layer = nn.Conv2d(c, out_channels, 1)
+        self.normalize_layer = nn.Identity()  # sparsemax has no parameters; it runs inside the decode kernel
+        self.probability_layers = _scalar_branch(in_channels, out_channels, nn.Sigmoid())
+        self.visibility_layers = _scalar_branch(in_channels, out_channels, nn.Sigmoid())
+        self.oks_layers = _scalar_branch(in_channels, out_channels, nn.Sigmoid())
+        self.error_layers = _scalar_branch(in_channels, out_channels, nn.ReLU())
+        self.init_weights()
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._cache = EngineCache(dict(embed_dim=in_channels, depth=0, heads=0, ffn_dim=0, num_keypoints=out_channels,
+                                       deconv_channels=deconv_out_channels[0], temperature=self.temperature,
+                                       normalize=normalize), precision)
+        self._named = None
+
+    @property
+    def default_init_cfg(self):
+        return [dict(type="Normal", layer=["Conv2d", "ConvTranspose2d"], std=0.001),
+                dict(type="Constant", layer="BatchNorm2d", val=1)]
+
+    def init_weights(self):  # probmap_head.py:590-598
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def engine_tensors(self, prefix: str = "head."):
+        if self._named is None or self._named[0] != prefix:
+            named = {prefix + k: v for k, v in self.named_parameters()}
+            named.update({prefix + k: v for k, v in self.named_buffers() if not k.endswith("num_batches_tracked")})
+            self._named = (prefix, named)
+        return self._named[1]
+
+    # ---- forward ----------------------------------------------------------------------
+    def _head_raw(self, x: torch.Tensor):
+        eng = self._cache.get(self.engine_tensors(), x.shape[0], x.device)
+        return eng.head(x.float().contiguous())
+
+    @torch.no_grad()
+    def forward(self, feats: Tuple[torch.Tensor]):
+        """probmap_head.py:600-625: (heatmaps (B,K,H,W) sparsemax-normalised and clamped,
+        probabilities, visibilities, oks, errors (B,K,1,1))."""
+        x = feats[-1]
+        logits, scal = self._head_raw(x)
+        _, heatmaps = ops.decode(logits, input_is_logits=True, temperature=self.temperature, normalize=self.normalize,
+                                 return_heatmaps=True)
+        b, k = scal.shape[0], scal.shape[2]
+        return (heatmaps,) + tuple(scal[:, j].reshape(b, k, 1, 1) for j in range(4))
+
+    def forward_heatmap(self, x: torch.Tensor) -> torch.Tensor:
+        return self.forward((x,))[0]
+
+    def pack_records(self, records: torch.Tensor) -> List[InstanceData]:
+        """Device records (B, K, 7) -> the reference's per-person ``InstanceData``
+        (probmap_head.py:776-798), with ONE device->host copy for the batch."""
+        rec = records.detach().cpu().numpy()
+        codec = self.decoder
+        if codec is None or not hasattr(codec, "keypoints_from_locs"):
+            raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__} (ProbMap codec required)")
+        kpts = codec.keypoints_from_locs(rec[:, :, :2])
+        preds = []
+        for i in range(rec.shape[0]):
+            p = InstanceData(keypoints=kpts[i][None], keypoint_scores=rec[i, :, 2][None])
+            p.set_field(p["keypoint_scores"], "keypoints_conf")
+            p.set_field(rec[i, :, 3][None], "keypoints_probs")
+            p.set_field(rec[i, :, 4][None], "keypoints_visible")
+            p.set_field(rec[i, :, 5][None], "keypoints_oks")
+            p.set_field(rec[i, :, 6][None], "keypoints_error")
+            if not self.freeze_oks:  # probmap_head.py:796-798
+                p.set_field(rec[i, :, 5][None], "keypoint_scores")
+            preds.append(p)
+        return preds
+
+    @staticmethod
+    def check_test_cfg(test_cfg: dict) -> None:
+        if test_cfg.get("flip_test", False):
+            if test_cfg.get("flip_mode", "heatmap") != "heatmap" or test_cfg.get("shift_heatmap", False):
+                raise NotImplementedError('flip_test is implemented for flip_mode="heatmap", shift_heatmap=False '
+                                          "(the shipped ProbPose test_cfg)")
+
+    @torch.no_grad()
+    def predict(self, feats, batch_data_samples, test_cfg: dict = {}):
+        """probmap_head.py:715-804.  Sparsemax, flip merge, decode and scalar merge run in one
+        kernel over both passes' raw outputs."""
+        self.check_test_cfg(test_cfg)
+        want_hm = bool(test_cfg.get("output_heatmaps", False))
+        if test_cfg.get("flip_test", False):
+            assert isinstance(feats, list) and len(feats) == 2
+            flip_indices = batch_data_samples[0].metainfo["flip_indices"]
+            x, xf = feats[0][-1], feats[1][-1]
+            b = x.shape[0]
+            logits, scal = self._head_raw(torch.cat([x, xf], 0))
+            out = ops.decode(logits[:b], logits[b:], flip_indices, scal[:b], scal[b:], input_is_logits=True,
+                             temperature=self.temperature, normalize=self.normalize, return_heatmaps=want_hm)
+        else:
+            logits, scal = self._head_raw(feats[-1])
+            out = ops.decode(logits, scalars=scal, input_is_logits=True, temperature=self.temperature,
+                             normalize=self.normalize, return_heatmaps=want_hm)
+        if want_hm:
+            records, heatmaps = out
+            return self.pack_records(records), [PixelData(heatmaps=hm) for hm in heatmaps.detach()]
+        return self.pack_records(out)
+
+    def loss(self, feats, batch_data_samples, train_cfg: dict = {}):
+        raise NotImplementedError("training (ProbMapHead.loss) is out of scope of the B200 inference path")

@@ -1,0 +1,99 @@
+"""Host logic of the MMPose-shaped plugin layer that needs no GPU: registry resolution, constructor
+contracts and error behaviour mirrored from the reference, checkpoint key layout, result packing."""
+import numpy as np
+import pytest
+import torch
+
+import probpose_code_b200.mmpose_api as api
+from probpose_code_b200 import synth
+
+
+def test_registry_resolves_the_config_type_strings():
+    assert api.MODELS.get("mmpretrain.VisionTransformer") is api.VisionTransformer
+    assert api.MODELS.get("VisionTransformer") is api.VisionTransformer
+    assert api.MODELS.get("ProbMapHead") is api.ProbMapHead
+    assert api.MODELS.get("TopdownPoseEstimator") is api.TopdownPoseEstimator
+    assert api.KEYPOINT_CODECS.get("ProbMap") is api.ProbMap
+    with pytest.raises(KeyError):
+        api.MODELS.build(dict(type="NoSuchThing"))
+    with pytest.raises(TypeError):
+        api.MODELS.build(dict(foo=1))
+
+
+def test_state_dict_layout_is_the_reference_checkpoint_layout():
+    model = api.MODELS.build(api.probpose_small_cfg())
+    sd = synth.make_state_dict(seed=0)
+    assert set(model.state_dict()) == set(sd)
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # witnesses from the reference: deconv weight is (Cin, Cout, 4, 4); head.test_cfg is a copy of the model's
+    assert model.head.deconv_layers[0].weight.shape == (384, 256, 4, 4)
+    assert model.head.deconv_layers[3].weight.shape == (256, 256, 4, 4)
+    assert model.head.test_cfg == model.test_cfg and model.head.test_cfg is not model.test_cfg
+    assert model.head.decoder.support_batch_decoding
+    names = model.head.engine_tensors()
+    assert "head.probability_layers.9.running_var" in names and not any(n.endswith("num_batches_tracked") for n in names)
+
+
+def test_constructor_errors_match_the_reference():
+    with pytest.raises(ValueError, match="same length"):  # probmap_head.py:211-217
+        api.ProbMapHead(in_channels=384, out_channels=17, deconv_out_channels=(256, 256), deconv_kernel_sizes=(4,),
+                        normalize=1.0, decoder=dict(type="ProbMap", input_size=(192, 256), heatmap_size=(48, 64)))
+    with pytest.raises(ValueError, match="heatmap_type"):  # probmap.py:91-96
+        api.ProbMap(input_size=(192, 256), heatmap_size=(48, 64), heatmap_type="nope")
+    with pytest.raises(NotImplementedError):  # outside the ProbPose configuration: loud, not silent
+        api.ProbMapHead(in_channels=384, out_channels=17, deconv_out_channels=(256, 256, 256), normalize=1.0,
+                        decoder=dict(type="ProbMap", input_size=(192, 256), heatmap_size=(48, 64)))
+    with pytest.raises(ValueError):
+        api.VisionTransformer(arch="nope", img_size=(256, 192), out_type="featmap", with_cls_token=False)
+    with pytest.raises(NotImplementedError):
+        api.VisionTransformer(arch="base", img_size=(256, 192))  # cls-token classifier configuration
+    head = api.ProbMapHead(in_channels=384, out_channels=17, deconv_out_channels=(256, 256), deconv_kernel_sizes=(4, 4),
+                           normalize=1.0, decoder=None)
+    with pytest.raises(RuntimeError, match="decoder has not been set"):  # base_head.py:50-55
+        head.decode(torch.zeros(1, 17, 64, 48))
+    with pytest.raises(NotImplementedError):
+        head.loss(None, None)
+    with pytest.raises(NotImplementedError):
+        head.check_test_cfg(dict(flip_test=True, flip_mode="udp_combined"))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from probpose_code_b200 import _lib
+    from probpose_code_b200.engine import Engine
+
+    with pytest.raises(_lib.PPError):
+        Engine(precision="fp16x3", max_batch=1)
+    model = api.MODELS.build(api.probpose_small_cfg())
+    with pytest.raises(Exception):
+        model.test_step(dict(inputs=[torch.zeros(3, 256, 192, dtype=torch.uint8)], data_samples=api.make_data_samples(1)))
+    from probpose_code_b200 import ops
+    with pytest.raises(_lib.PPError):
+        ops.decode(torch.zeros(1, 17, 64, 48), input_is_logits=False)
+
+
+def test_pack_records_and_image_space_mapping():
+    model = api.MODELS.build(api.probpose_small_cfg())
+    rec = torch.zeros(2, 17, 7)
+    rec[..., 0], rec[..., 1] = 47.0, 63.0  # bottom-right heatmap pixel
+    rec[..., 2], rec[..., 3], rec[..., 4], rec[..., 5], rec[..., 6] = 0.9, 0.8, 0.7, 0.6, 0.5
+    preds = model.head.pack_records(rec)
+    p = preds[0]
+    assert p.keypoints.shape == (1, 17, 2) and p.keypoints.dtype == np.float64
+    np.testing.assert_allclose(p.keypoints[0, 0], [192.0, 256.0])  # probmap.py:218: / (W-1, H-1) * input_size
+    assert p.keypoint_scores.shape == (1, 17) and p.keypoint_scores.dtype == np.float32
+    np.testing.assert_allclose(p.keypoint_scores, 0.6)  # replaced by oks (freeze_oks=False), probmap_head.py:796-798
+    np.testing.assert_allclose(p.keypoints_conf, 0.9)
+    np.testing.assert_allclose(p.keypoints_probs, 0.8)
+    np.testing.assert_allclose(p.keypoints_visible, 0.7)
+    np.testing.assert_allclose(p.keypoints_error, 0.5)
+    samples = api.make_data_samples(2)
+    samples[1].set_metainfo(dict(input_center=np.array([500.0, 400.0]), input_scale=np.array([96.0, 128.0])))
+    out = model.add_pred_to_datasample(preds, None, samples)
+    np.testing.assert_allclose(out[0].pred_instances.keypoints[0, 0], [192.0, 256.0])
+    # topdown.py:165-167: kpts / input_size * input_scale + input_center - 0.5 * input_scale
+    np.testing.assert_allclose(out[1].pred_instances.keypoints[0, 0], [192 / 192 * 96 + 500 - 48, 256 / 256 * 128 + 400 - 64])
+    assert out[1].pred_instances.bboxes.shape == (1, 4)
