@@ -125,6 +125,18 @@ typedef struct pp_gemm_args {
   int32_t tile_n;         /* 0 = auto; else 32/64/128/192/256 output-tile width (tuning)   */
   int32_t res_mod;        /* > 0: the residual has res_mod rows and output row r adds row
                              r % res_mod (pos_embed broadcast over the batch); 0 = (M, ldd)  */
+  /* Implicit-GEMM convolution ("taps"), no im2col copy.  With a_taps > 1 the A operand has
+   * logical width k / a_taps and its rows enumerate a ZERO-PADDED NHWC map (b, in_h + 2, in_w + 2);
+   * K-group t is that operand read at row offset a_tap_shift[t] = dy * (in_w + 2) + dx (rows outside
+   * the operand read as zero), so A.W^T is a 3x3 convolution / one ConvTranspose2d sub-pixel phase
+   * evaluated at every padded position.  in_pad = 1 then drops the border rows and maps interior
+   * row (b, i + 1, j + 1) to output row (b, i, j) (or through the up_* scatter).  out_pad = 1
+   * writes into an output map that itself carries a one-pixel border (left untouched: the
+   * caller zeroes it once), ready to be the tap operand of the next layer.                    */
+  int32_t a_taps;         /* 0 / 1 = plain operand                                          */
+  int32_t a_tap_shift[9];
+  int32_t in_pad, in_h, in_w; /* in_h / in_w also required by up_* when in_pad = 1           */
+  int32_t out_pad;
 } pp_gemm_args;
 
 PP_API int pp_gemm(const pp_gemm_args* args, void* stream);

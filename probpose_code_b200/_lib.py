@@ -38,7 +38,9 @@ class GemmArgs(C.Structure):
                 ("a", C.c_void_p), ("w", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("residual", C.c_void_p), ("act", C.c_int32), ("out_kind", C.c_int32), ("d", C.c_void_p),
                 ("ldd", C.c_int32), ("plane", C.c_int32), ("up_hin", C.c_int32), ("up_win", C.c_int32),
-                ("up_py", C.c_int32), ("up_px", C.c_int32), ("tile_n", C.c_int32), ("res_mod", C.c_int32)]
+                ("up_py", C.c_int32), ("up_px", C.c_int32), ("tile_n", C.c_int32), ("res_mod", C.c_int32),
+                ("a_taps", C.c_int32), ("a_tap_shift", C.c_int32 * 9), ("in_pad", C.c_int32), ("in_h", C.c_int32),
+                ("in_w", C.c_int32), ("out_pad", C.c_int32)]
 
 
 class EngineCfg(C.Structure):

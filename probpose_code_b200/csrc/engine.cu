@@ -217,6 +217,9 @@ static int validate_cfg(const pp_engine_cfg* c) {
                PP_ERR_UNSUPPORTED, "heads %d: head width must be 32 or 64", c->heads);
     PP_REQUIRE(c->ffn_dim > 0 && c->ffn_dim % 64 == 0, PP_ERR_UNSUPPORTED, "ffn_dim %d must be a multiple of 64", c->ffn_dim);
     PP_REQUIRE((3 * c->patch * c->patch) % 64 == 0, PP_ERR_UNSUPPORTED, "patch %d: 3*patch^2 must be a multiple of 64", c->patch);
+    const int tok = ((c->img_h + 2 * c->patch_pad - c->patch) / c->patch + 1) * ((c->img_w + 2 * c->patch_pad - c->patch) / c->patch + 1);
+    PP_REQUIRE(c->precision == PP_PREC_FP32_SIMT || attention_mma_supported(tok, c->embed_dim / c->heads), PP_ERR_UNSUPPORTED,
+               "tensor-core attention is built for 192 tokens (256x192 crops, patch 16, pad 2); this geometry has %d", tok);
   }
   PP_REQUIRE(c->depth > 0 || c->deconv_channels > 0, PP_ERR_INVALID, "engine has neither a backbone nor a head");
   if (c->deconv_channels > 0) {
@@ -300,8 +303,13 @@ static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int ba
                             nullptr, st); }));
     pp_gemm_args g = gemm_args(e, M, 3 * D, D, e->at<>(e->a_op), e->at<>(L.wqkv));
     g.shift = e->P(p + "attn.qkv.bias"); g.d = e->at<>(e->qkv);
+    const bool tc_attn = prec != PP_PREC_FP32_SIMT;  // q, k, v leave the GEMM pre-split for the tensor-core attention
+    if (tc_attn) { g.out_kind = PP_OUT_OPERAND; g.ldd = 3 * D; }
     PP_TRY(gemm(e, g, st));
-    PP_TRY(timed(e, PP_KC_ATTENTION, st, [&] { return launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st); }));
+    PP_TRY(timed(e, PP_KC_ATTENTION, st, [&] {
+      return tc_attn ? launch_attention_mma(prec, e->at<>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st)
+                     : launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st);
+    }));
     g = gemm_args(e, M, D, D, e->at<>(e->a_op), e->at<>(L.wproj));
     g.shift = e->P(p + "attn.proj.bias"); g.residual = x; g.d = x;
     PP_TRY(gemm(e, g, st));

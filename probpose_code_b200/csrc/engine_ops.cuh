@@ -26,6 +26,11 @@ int launch_layernorm(int prec, const float* x, const float* gamma, const float* 
 // Global multi-head attention on packed qkv fp32 (B * n, 3 * heads * dh) -> operand (B * n, heads * dh).
 int launch_attention(int prec, const float* qkv, int batch, int n, int heads, int dh, void* out_op, cudaStream_t st);
 
+// Tensor-core attention (attention.cu): qkv_op is the qkv GEMM's PP_OUT_OPERAND output
+// (B * n, 3 * heads * dh) in `prec`; out_op the proj GEMM's A operand.
+bool attention_mma_supported(int n, int dh);
+int launch_attention_mma(int prec, const void* qkv_op, int batch, int n, int heads, int dh, void* out_op, cudaStream_t st);
+
 // fp32 token rows (B * hw, c) <-> fp32 NCHW (B, c, hw); NCHW -> operand rows.
 int launch_rows_to_nchw(const float* rows, int batch, int hw, int c, float* nchw, cudaStream_t st);
 int launch_nchw_to_operand(int prec, const float* nchw, int batch, int hw, int c, void* rows_op, cudaStream_t st);

@@ -14,7 +14,8 @@ struct EpiParams {
   void* d;
   int m, n;
   int act, out_kind, ldd, plane;
-  int up_hin, up_win, up_py, up_px;
+  int up_hin, up_py, up_px;        // up_hin != 0: stride-2 ConvTranspose2d phase scatter
+  int in_h, in_w, in_pad, out_pad;  // geometry of the map the GEMM rows enumerate (see map_out_row)
   int res_mod;
 };
 
@@ -24,14 +25,31 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// Logical GEMM row -> output row (identity, or sub-pixel phase scatter of a stride-2 deconv).
-__device__ __forceinline__ int64_t epi_out_row(const EpiParams& e, int m) {
-  if (e.up_hin == 0) return m;
-  const int j = m % e.up_win;
-  const int t = m / e.up_win;
-  const int i = t % e.up_hin;
-  const int b = t / e.up_hin;
-  return (int64_t)(b * 2 * e.up_hin + 2 * i + e.up_py) * (2 * e.up_win) + 2 * j + e.up_px;
+// Logical GEMM row -> output row and validity.
+//   in_pad : the A rows enumerate a zero-padded (in_h + 2) x (in_w + 2) map; border rows produce nothing
+//   up     : stride-2 ConvTranspose2d phase scatter (i, j) -> (2 i + py, 2 j + px)
+//   out_pad: the output map carries a one-pixel zero border of its own (it feeds the next tap GEMM)
+__device__ __forceinline__ int64_t map_out_row(const EpiParams& e, int m, bool& valid) {
+  valid = m < e.m;
+  if (e.up_hin == 0 && e.in_pad == 0 && e.out_pad == 0) return m;
+  int b, i, j;
+  if (e.in_pad) {
+    const int wp = e.in_w + 2, hp = e.in_h + 2;
+    const int jp = m % wp, t = m / wp;
+    const int ip = t % hp;
+    b = t / hp;
+    valid = valid && jp >= 1 && jp <= e.in_w && ip >= 1 && ip <= e.in_h;
+    i = ip - 1; j = jp - 1;
+  } else {
+    j = m % e.in_w;
+    const int t = m / e.in_w;
+    i = t % e.in_h;
+    b = t / e.in_h;
+  }
+  const int op = e.out_pad;
+  if (e.up_hin)
+    return (int64_t)(b * (2 * e.in_h + 2 * op) + 2 * i + e.up_py + op) * (2 * e.in_w + 2 * op) + 2 * j + e.up_px + op;
+  return (int64_t)(b * (e.in_h + 2 * op) + i + op) * (e.in_w + 2 * op) + j + op;
 }
 
 // Finish and store NC consecutive columns [n0, n0 + NC) of logical row m (m < e.m checked by
@@ -40,7 +58,9 @@ template <int PREC, int NC>
 __device__ __forceinline__ void epi_store(const EpiParams& e, int m, int n0, float (&v)[NC], const float* sc,
                                           const float* sh) {
   static_assert(NC % 4 == 0, "column chunk must be a multiple of 4");
-  const int64_t orow = epi_out_row(e, m);
+  bool row_ok;
+  const int64_t orow = map_out_row(e, m, row_ok);
+  if (!row_ok) return;
   const bool full = (n0 + NC <= e.n);
 #pragma unroll
   for (int c = 0; c < NC; ++c) v[c] = apply_act(fmaf(v[c], sc[c], sh[c]), e.act);

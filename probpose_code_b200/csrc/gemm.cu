@@ -10,8 +10,10 @@ int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaSt
 // Exists to verify the tensor-core path on the GPU itself (same epilogue, same layouts).
 constexpr int kSB = 64, kSK = 16;
 
+struct SimtTaps { int taps, tap_k; int shift[9]; };
+
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ W, int K,
-                                                        const EpiParams e) {
+                                                        const SimtTaps tp, const EpiParams e) {
   __shared__ float sA[kSK][kSB + 4];
   __shared__ float sW[kSK][kSB + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -20,7 +22,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   for (int k0 = 0; k0 < K; k0 += kSK) {
     for (int i = threadIdx.x; i < kSB * kSK; i += 256) {
       const int r = i / kSK, c = i % kSK;
-      sA[c][r] = (m0 + r < e.m) ? A[(int64_t)(m0 + r) * K + k0 + c] : 0.f;
+      const int kg = k0 + c, tap = kg / tp.tap_k;
+      const int64_t ar = (int64_t)m0 + r + tp.shift[tap];  // tap operands: shifted source row, zero outside
+      sA[c][r] = (m0 + r < e.m && ar >= 0 && ar < e.m) ? A[ar * tp.tap_k + (kg - tap * tp.tap_k)] : 0.f;
       sW[c][r] = (n0 + r < e.n) ? W[(int64_t)(n0 + r) * K + k0 + c] : 0.f;
     }
     __syncthreads();
@@ -90,11 +94,19 @@ int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st) {
   EpiParams e;
   e.scale = a.scale; e.shift = a.shift; e.residual = a.residual; e.d = a.d;
   e.m = a.m; e.n = a.n; e.act = a.act; e.out_kind = a.out_kind; e.ldd = a.ldd; e.plane = a.plane;
-  e.up_hin = a.up_hin; e.up_win = a.up_win; e.up_py = a.up_py; e.up_px = a.up_px;
+  e.up_hin = a.up_hin; e.up_py = a.up_py; e.up_px = a.up_px;
+  e.in_pad = a.in_pad; e.out_pad = a.out_pad;
+  e.in_h = a.in_pad ? a.in_h : a.up_hin; e.in_w = a.in_pad ? a.in_w : a.up_win;
+  if (a.out_pad && !a.in_pad && !a.up_hin) { e.in_h = a.in_h; e.in_w = a.in_w; }
   e.res_mod = a.res_mod;
   if (a.precision == PP_PREC_FP32_SIMT) {
+    SimtTaps tp = {};
+    tp.taps = a.a_taps > 1 ? a.a_taps : 1;
+    PP_REQUIRE(tp.taps <= 9 && a.k % tp.taps == 0, PP_ERR_INVALID, "pp_gemm: %d taps do not divide k=%d", tp.taps, a.k);
+    tp.tap_k = a.k / tp.taps;
+    for (int t = 0; t < tp.taps; ++t) tp.shift[t] = a.a_taps > 1 ? a.a_tap_shift[t] : 0;
     dim3 grid((a.n + kSB - 1) / kSB, (a.m + kSB - 1) / kSB);
-    gemm_simt_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a.a), reinterpret_cast<const float*>(a.w), a.k, e);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(a.a), reinterpret_cast<const float*>(a.w), a.k, tp, e);
     count_launch();
     PP_CHECK_CUDA(cudaGetLastError());
     return PP_OK;
@@ -115,5 +127,11 @@ extern "C" int pp_gemm(const pp_gemm_args* a, void* stream) {
   PP_REQUIRE(a->out_kind != PP_OUT_OPERAND || (a->ldd % 4 == 0 && a->residual == nullptr), PP_ERR_INVALID,
              "pp_gemm: operand output needs ldd %% 4 == 0 and no residual");
   PP_REQUIRE(a->res_mod >= 0, PP_ERR_INVALID, "pp_gemm: res_mod=%d", a->res_mod);
+  PP_REQUIRE(a->a_taps >= 0 && a->a_taps <= 9, PP_ERR_INVALID, "pp_gemm: a_taps=%d outside [0, 9]", a->a_taps);
+  PP_REQUIRE((!a->in_pad && !(a->out_pad && !a->up_hin)) || (a->in_h > 0 && a->in_w > 0), PP_ERR_INVALID,
+             "pp_gemm: in_pad / out_pad need in_h, in_w > 0");
+  PP_REQUIRE(!a->up_hin || a->up_win > 0, PP_ERR_INVALID, "pp_gemm: up_hin without up_win");
+  PP_REQUIRE(!(a->up_hin && a->in_pad) || (a->up_hin == a->in_h && a->up_win == a->in_w), PP_ERR_INVALID,
+             "pp_gemm: up_hin/up_win must equal in_h/in_w when in_pad is set");
   return gemm_dispatch(*a, (cudaStream_t)stream);
 }

@@ -1,12 +1,16 @@
 // tcgen05 tensor-core GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] . W[N,K]^T), fp32 accumulate.
 //
-// One 128 x BN output tile per CTA, warp-specialised:
+// Persistent, warp-specialised: one CTA per SM walks the 128 x BN output tiles (n fastest, so the
+// CTAs running together share their A rows in L2) and keeps three pipelines busy at once:
 //   warp 0      TMA producer  - cp.async.bulk.tensor (128-byte swizzle) of A / W k-blocks into a
 //                               STAGES-deep shared-memory ring, completion on mbarriers
 //   warp 1      MMA issuer    - one thread issues tcgen05.mma (M=128, N=BN, K=16) per 32-byte
-//                               k-slice; accumulators live in TMEM; tcgen05.commit frees the slot
-//   warps 2..5  epilogue      - tcgen05.ld 32 lanes x 32 columns -> registers -> scale/shift/
-//                               activation/residual -> global (fp32 rows, next operand, or planes)
+//                               k-slice into one of TWO TMEM accumulator stages; tcgen05.commit
+//                               frees the smem slot / publishes the accumulator
+//   warps 2..9  epilogue      - drain the other accumulator stage while the next tile's MMAs run:
+//                               tcgen05.ld (32 lanes x 32 columns) -> registers -> swizzled smem
+//                               transpose -> scale/shift/activation/residual on float4 row segments
+//                               -> coalesced global stores (fp32 rows, next operand, or planes)
 //
 // Precision modes (pp_precision):
 //   FP16 / BF16  one MMA per k-slice.
@@ -28,8 +32,21 @@ namespace pp {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 x 16-bit = 128 bytes = one swizzle row
-constexpr int kGemmThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
+constexpr int kStagingBytes = kEpiWarps * 4096;    // one 32 x 32 fp32 transpose tile per epilogue warp
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kMaxTaps = 9;
+
+// Implicit-GEMM A operand ("taps"): K is split into `taps` groups of `tap_k` columns; group t is
+// read from the SAME source operand (row width tap_k) at row offset shift[t].  The source rows
+// enumerate a zero-padded NHWC map, so a constant row shift is a spatial (dy, dx) shift and
+// conv / deconv-phase GEMMs need no gathered copy of their input.  taps == 1: plain operand.
+struct TapParams {
+  int taps;
+  int tap_k;
+  int shift[kMaxTaps];
+};
 
 template <int BN, int SPLIT>
 struct GemmCfg {
@@ -37,40 +54,51 @@ struct GemmCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
-  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_COLS = NOPS * BN;
-  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-  // ring | full[STAGES] empty[STAGES] tmem_full | tmem ptr | scale[BN] shift[BN] | 1024 B alignment slack
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+  static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_NEED = ACC_STAGES * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int MISC_BYTES = 256;  // barriers + tmem pointer
+  static constexpr int RING_BUDGET = kSmemMax - 1024 - kStagingBytes - MISC_BYTES;
+  static constexpr int STAGES_RAW = RING_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // ring | staging | full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] | tmem ptr | 1024 B alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + MISC_BYTES + 1024;
   static_assert(STAGES >= 2, "tile too large for a 2-stage ring");
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert((2 * STAGES + 4) * 8 + 16 <= MISC_BYTES, "barrier block too small");
+  static_assert(BN % 32 == 0, "epilogue works on 32-column chunks");
 };
+
+__device__ __forceinline__ float4 act4(float4 v, int act) {
+  v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+  return v;
+}
 
 template <int BN, int SPLIT, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const int K,
-               const EpiParams e) {
+               const int num_m_tiles, const int num_n_tiles, const TapParams tp, const EpiParams e) {
   using Cfg = GemmCfg<BN, SPLIT>;
   constexpr int PREC = SPLIT == 3 ? PP_PREC_FP16X3 : (BF16 ? PP_PREC_BF16 : PP_PREC_FP16);
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float4* staging = reinterpret_cast<float4*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(tmem_ptr + 4);
-  float* s_shift = s_scale + BN;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   auto stage_a = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + part * Cfg::A_BYTES; };
   auto stage_b = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::A_BYTES + part * Cfg::B_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
   const int num_kb = K / kBK;
+  const int num_tiles = num_m_tiles * num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
@@ -79,7 +107,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full_bar[s], 1);
+      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -94,16 +125,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        ptx::tma_load_2d(stage_a(s, 0), &tm_a, &full_bar[s], kb * kBK, m0);
-        ptx::tma_load_2d(stage_b(s, 0), &tm_w, &full_bar[s], kb * kBK, n0);
-        if constexpr (SPLIT == 3) {
-          ptx::tma_load_2d(stage_a(s, 1), &tm_a, &full_bar[s], K + kb * kBK, m0);
-          ptx::tma_load_2d(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * kBK, n0);
+      const int kb_per_tap = tp.tap_k / kBK;
+      const int a_lo = tp.tap_k;  // column of the lo plane inside an FP16X3 A row
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * kBM, n0 = (tile % num_n_tiles) * BN;
+        int tap = 0, kc = 0;  // current tap and its k-block
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          const int arow = m0 + tp.shift[tap];
+          ptx::tma_load_2d(stage_a(s, 0), &tm_a, &full_bar[s], kc * kBK, arow);
+          ptx::tma_load_2d(stage_b(s, 0), &tm_w, &full_bar[s], kb * kBK, n0);
+          if constexpr (SPLIT == 3) {
+            ptx::tma_load_2d(stage_a(s, 1), &tm_a, &full_bar[s], a_lo + kc * kBK, arow);
+            ptx::tma_load_2d(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * kBK, n0);
+          }
+          if (++kc == kb_per_tap) { kc = 0; ++tap; }
         }
       }
     }
@@ -111,56 +151,154 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, kBM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt % ACC_STAGES;
+        const uint32_t aph = (lt / ACC_STAGES) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);  // epilogue has drained this accumulator stage
         ptx::tcgen05_fence_after();
-        const uint32_t a_hi = ptx::smem_u32(stage_a(s, 0)), b_hi = ptx::smem_u32(stage_b(s, 0));
+        const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tcgen05_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(stage_a(s, 0)), b_hi = ptx::smem_u32(stage_b(s, 0));
 #pragma unroll
-        for (int kk = 0; kk < kBK / 16; ++kk) {
-          const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-          const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + kk * 32);
-          const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + kk * 32);
-          ptx::umma_f16(tmem_base, da, db, idesc, acc);
-          if constexpr (SPLIT == 3) {
-            const uint64_t da_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(stage_a(s, 1)) + kk * 32);
-            const uint64_t db_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(stage_b(s, 1)) + kk * 32);
-            ptx::umma_f16(tmem_base + BN, da, db_lo, idesc, acc);
-            ptx::umma_f16(tmem_base + BN, da_lo, db, idesc, 1u);
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+            const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + kk * 32);
+            const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + kk * 32);
+            ptx::umma_f16(acc0, da, db, idesc, acc);
+            if constexpr (SPLIT == 3) {
+              const uint64_t da_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(stage_a(s, 1)) + kk * 32);
+              const uint64_t db_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(stage_b(s, 1)) + kk * 32);
+              ptx::umma_f16(acc0 + BN, da, db_lo, idesc, acc);
+              ptx::umma_f16(acc0 + BN, da_lo, db, idesc, 1u);
+            }
           }
+          ptx::umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
         }
-        ptx::umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator stage complete
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulators complete
     }
   } else {
-    // ===== epilogue (128 threads) =====
-    const int et = threadIdx.x - 64;
-    for (int c = et; c < BN; c += 128) {
-      const bool in = n0 + c < e.n;
-      s_scale[c] = (in && e.scale) ? e.scale[n0 + c] : 1.f;
-      s_shift[c] = (in && e.shift) ? e.shift[n0 + c] : 0.f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tcgen05_fence_after();
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      ptx::tmem_ld_32x32b_x32(lane_base + c0, v);
-      if constexpr (SPLIT == 3) {
-        float w[32];
-        ptx::tmem_ld_32x32b_x32(lane_base + BN + c0, w);
+    // ===== epilogue (8 warps): two warps share a TMEM lane quarter and split its column chunks =====
+    const int ew = warp - 2;
+    const int q = warp & 3;     // TMEM lane quarter this warp may access
+    const int half = ew >> 2;   // which of the quarter's two warps
+    float4* stg = staging + ew * 256;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int c4 = lane & 7, rsub = lane >> 3;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / num_n_tiles) * kBM, n0 = (tile % num_n_tiles) * BN;
+      const int as = lt % ACC_STAGES;
+      const uint32_t aph = (lt / ACC_STAGES) & 1;
+      const int row_base = m0 + q * 32;
+      // output rows of the 8 row slots this lane stores (row_base + i * 4 + rsub)
+      int64_t orow[8];
+      uint32_t vmask = 0;
+      if (e.out_kind != PP_OUT_PLANES) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], kLoScaleInv, v[i]);
+        for (int i = 0; i < 8; ++i) {
+          bool ok;
+          orow[i] = map_out_row(e, row_base + i * 4 + rsub, ok);
+          vmask |= ok ? (1u << i) : 0u;
+        }
       }
-      if (row < e.m && n0 + c0 < e.n) epi_store<PREC, 32>(e, row, n0 + c0, v, s_scale + c0, s_shift + c0);
+      ptx::mbar_wait(&tmem_full_bar[as], aph);
+      ptx::tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + as * Cfg::ACC_COLS + lane_off;
+#pragma unroll 1
+      for (int ch = half; ch < BN / 32; ch += 2) {
+        const int c0 = ch * 32;
+        float v[32];
+        ptx::tmem_ld_32x32b_x32(tacc + c0, v);
+        if constexpr (SPLIT == 3) {
+          float w[32];
+          ptx::tmem_ld_32x32b_x32(tacc + BN + c0, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], kLoScaleInv, v[i]);
+        }
+        if (ch + 2 >= BN / 32) {  // last TMEM read of this tile: hand the accumulator stage back
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        }
+        if (n0 + c0 >= e.n) continue;
+        if (e.out_kind == PP_OUT_PLANES) {
+          // (M / plane, N, plane): lanes are consecutive pixels of one plane -> already coalesced
+          const int row = row_base + lane;
+          if (row < e.m) {
+            const int64_t img = row / e.plane, pix = row % e.plane;
+            float* dbase = reinterpret_cast<float*>(e.d) + (img * e.n + n0 + c0) * e.plane + pix;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int n = n0 + c0 + c;
+              if (n < e.n) {
+                const float sc = e.scale ? __ldg(e.scale + n) : 1.f, sh = e.shift ? __ldg(e.shift + n) : 0.f;
+                dbase[(int64_t)c * e.plane] = apply_act(fmaf(v[c], sc, sh), e.act);
+              }
+            }
+          }
+          continue;
+        }
+        // transpose through swizzled shared memory: lane (row) writes 8 float4, then each lane
+        // reads float4 column c4 of rows i * 4 + rsub -> 128-byte row segments per 8 lanes
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + c0 + c4 * 4;
+        if (col + 4 <= e.n && (e.ldd & 3) == 0) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e.scale) sc = __ldg(reinterpret_cast<const float4*>(e.scale + col));
+          if (e.shift) sh = __ldg(reinterpret_cast<const float4*>(e.shift + col));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!((vmask >> i) & 1u)) continue;
+            const int r = i * 4 + rsub;
+            float4 x = stg[r * 8 + (c4 ^ (r & 7))];
+            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+            x = act4(x, e.act);
+            if (e.out_kind == PP_OUT_F32) {
+              float* dp = reinterpret_cast<float*>(e.d) + orow[i] * e.ldd + col;
+              if (e.residual) {
+                const float4 rr = *reinterpret_cast<const float4*>(e.residual + (e.res_mod > 0 ? orow[i] % e.res_mod : orow[i]) * e.ldd + col);
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+              }
+              *reinterpret_cast<float4*>(dp) = x;
+            } else {
+              store_operand4<PREC>(e.d, orow[i], col, e.ldd, x);
+            }
+          }
+        } else if (col < e.n) {  // ragged right edge (n % 4 != 0): scalar
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!((vmask >> i) & 1u)) continue;
+            const int r = i * 4 + rsub;
+            const float4 x4 = stg[r * 8 + (c4 ^ (r & 7))];
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+            for (int c = 0; c < 4 && col + c < e.n; ++c) {
+              const float sc = e.scale ? __ldg(e.scale + col + c) : 1.f, sh = e.shift ? __ldg(e.shift + col + c) : 0.f;
+              float x = apply_act(fmaf(xs[c], sc, sh), e.act);
+              if (e.out_kind == PP_OUT_F32) {
+                if (e.residual) x += e.residual[(e.res_mod > 0 ? orow[i] % e.res_mod : orow[i]) * e.ldd + col + c];
+                reinterpret_cast<float*>(e.d)[orow[i] * e.ldd + col + c] = x;
+              } else {
+                store_operand<PREC>(e.d, orow[i], col + c, e.ldd, x);
+              }
+            }
+          }
+        }
+        __syncwarp();  // staging tile is rewritten by the next chunk
+      }
+      if (half >= BN / 32) {  // this warp had no chunk (BN == 32): still release the stage
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+      }
     }
-    ptx::tcgen05_fence_before();
   }
 
   __syncthreads();
@@ -219,8 +357,18 @@ static int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, in
   return PP_OK;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int BN, int SPLIT, bool BF16>
-static int launch_tc(const pp_gemm_args& a, const EpiParams& e, cudaStream_t st) {
+static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SPLIT>;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, SPLIT, BF16>;
@@ -228,27 +376,29 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, cudaStream_t st)
     PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int64_t row_elems = (SPLIT == 3 ? 2 : 1) * (int64_t)a.k;
+  const int nops = SPLIT == 3 ? 2 : 1;
   CUtensorMap tma, tmw;
-  int rc = make_operand_map(&tma, a.a, a.m, row_elems, kBM, BF16);
+  int rc = make_operand_map(&tma, a.a, a.m, (int64_t)nops * tp.tap_k, kBM, BF16);
   if (rc) return rc;
-  rc = make_operand_map(&tmw, a.w, a.n, row_elems, BN, BF16);
+  rc = make_operand_map(&tmw, a.w, a.n, (int64_t)nops * a.k, BN, BF16);
   if (rc) return rc;
-  dim3 grid((a.n + BN - 1) / BN, (a.m + kBM - 1) / kBM);
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tma, tmw, a.k, e);
+  const int mt = (a.m + kBM - 1) / kBM, nt = (a.n + BN - 1) / BN;
+  const int64_t tiles = (int64_t)mt * nt;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tma, tmw, a.k, mt, nt, tp, e);
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
 }
 
 template <int SPLIT, bool BF16>
-static int launch_tc_bn(int bn, const pp_gemm_args& a, const EpiParams& e, cudaStream_t st) {
+static int launch_tc_bn(int bn, const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
   switch (bn) {
-    case 32: return launch_tc<32, SPLIT, BF16>(a, e, st);
-    case 64: return launch_tc<64, SPLIT, BF16>(a, e, st);
-    case 128: return launch_tc<128, SPLIT, BF16>(a, e, st);
-    case 192: return launch_tc<192, SPLIT, BF16>(a, e, st);
-    case 256: return launch_tc<256, SPLIT, BF16>(a, e, st);
+    case 32: return launch_tc<32, SPLIT, BF16>(a, e, tp, st);
+    case 64: return launch_tc<64, SPLIT, BF16>(a, e, tp, st);
+    case 128: return launch_tc<128, SPLIT, BF16>(a, e, tp, st);
+    case 192: return launch_tc<192, SPLIT, BF16>(a, e, tp, st);
+    case 256: return launch_tc<256, SPLIT, BF16>(a, e, tp, st);
   }
   set_error("pp_gemm: unsupported tile_n %d", bn);
   return PP_ERR_INVALID;
@@ -257,7 +407,7 @@ static int launch_tc_bn(int bn, const pp_gemm_args& a, const EpiParams& e, cudaS
 static int pick_tile_n(int n, int prec) {
   if (n <= 32) return 32;
   if (n <= 64) return 64;
-  if (prec == PP_PREC_FP16X3) return (n % 128 == 0 || n > 192) ? 128 : 192;
+  if (prec == PP_PREC_FP16X3) return 128;  // 2 accumulators x 128 columns x 2 TMEM stages = 512 columns
   if (n % 256 == 0) return 256;
   if (n % 192 == 0) return 192;
   return 128;
@@ -265,11 +415,17 @@ static int pick_tile_n(int n, int prec) {
 
 int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaStream_t st) {
   PP_REQUIRE(a.k % kBK == 0 && a.k > 0, PP_ERR_INVALID, "pp_gemm: k=%d must be a positive multiple of %d", a.k, kBK);
+  TapParams tp = {};
+  tp.taps = a.a_taps > 1 ? a.a_taps : 1;
+  PP_REQUIRE(tp.taps <= kMaxTaps && a.k % tp.taps == 0 && (a.k / tp.taps) % kBK == 0, PP_ERR_INVALID,
+             "pp_gemm: %d taps need k=%d to split into multiples of %d", tp.taps, a.k, kBK);
+  tp.tap_k = a.k / tp.taps;
+  for (int t = 0; t < tp.taps; ++t) tp.shift[t] = a.a_taps > 1 ? a.a_tap_shift[t] : 0;
   const int bn = tile_n > 0 ? tile_n : pick_tile_n(a.n, a.precision);
   switch (a.precision) {
-    case PP_PREC_FP16X3: return launch_tc_bn<3, false>(bn, a, e, st);
-    case PP_PREC_BF16: return launch_tc_bn<1, true>(bn, a, e, st);
-    case PP_PREC_FP16: return launch_tc_bn<1, false>(bn, a, e, st);
+    case PP_PREC_FP16X3: return launch_tc_bn<3, false>(bn, a, e, tp, st);
+    case PP_PREC_BF16: return launch_tc_bn<1, true>(bn, a, e, tp, st);
+    case PP_PREC_FP16: return launch_tc_bn<1, false>(bn, a, e, tp, st);
   }
   set_error("pp_gemm: precision %d is not a tensor-core mode", a.precision);
   return PP_ERR_INVALID;

@@ -87,18 +87,23 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
          scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE, out_kind: int = _lib.OUT_F32,
          out: Optional[torch.Tensor] = None, ldd: Optional[int] = None, plane: int = 0, up=None, tile_n: int = 0,
-         res_mod: int = 0):
+         res_mod: int = 0, taps: Optional[Sequence[int]] = None, in_pad=None, out_pad: bool = False,
+         out_rows: Optional[int] = None):
     """``pp_gemm``: D = epilogue(A . W^T).  ``a_op`` / ``w_op`` are operand buffers from
-    :func:`to_operand`.  Returns the output tensor (fp32, or a uint8 operand buffer)."""
+    :func:`to_operand`.  Returns the output tensor (fp32, or a uint8 operand buffer).
+
+    ``taps``: row shifts of the implicit-GEMM A operand (logical width ``k / len(taps)``);
+    ``in_pad=(h, w)``: the A rows enumerate a zero-padded ``(h + 2, w + 2)`` map; ``out_pad``:
+    the output map carries a border too; ``out_rows``: rows of a freshly allocated output."""
     dev = a_op.device
     if out_kind == _lib.OUT_F32:
         ldd = n if ldd is None else ldd
-        rows = m if up is None else m * 4
+        rows = out_rows if out_rows is not None else (m if up is None else m * 4)
         if out is None:
-            out = torch.empty((rows, ldd), dtype=torch.float32, device=dev)
+            out = torch.zeros((rows, ldd), dtype=torch.float32, device=dev)
     elif out_kind == _lib.OUT_OPERAND:
         ldd = n if ldd is None else ldd
-        rows = m if up is None else m * 4
+        rows = out_rows if out_rows is not None else (m if up is None else m * 4)
         if out is None:
             out = torch.zeros(lib().pp_operand_bytes(precision, rows, ldd), dtype=torch.uint8, device=dev)
     else:
@@ -107,8 +112,12 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
         if out is None:
             out = torch.empty((m // plane, n, plane), dtype=torch.float32, device=dev)
     hin, win, py, px = up if up is not None else (0, 0, 0, 0)
+    ntaps = 0 if taps is None else len(taps)
+    shifts = (C.c_int32 * 9)(*([int(t) for t in taps] + [0] * (9 - ntaps))) if taps is not None else (C.c_int32 * 9)()
+    ih, iw = in_pad if in_pad is not None else (0, 0)
     args = _lib.GemmArgs(precision, m, n, k, a_op.data_ptr(), w_op.data_ptr(), _ptr(scale), _ptr(shift),
-                         _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n, res_mod)
+                         _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n, res_mod,
+                         ntaps, shifts, int(in_pad is not None), ih, iw, int(out_pad))
     with torch.cuda.device(dev):
         check(lib().pp_gemm(C.byref(args), _stream()), "pp_gemm")
     return out
