@@ -70,6 +70,7 @@ struct pp_engine {
   size_t w_c1, w_c2[4], w_c3[4], c_scale[3], c_shift[3], tail_w, tail_b;
   // activations (byte offsets)
   size_t x, a_op, qkv, h_op, feat_op, feat_f32;
+  size_t feat_bytes = 0, d1_bytes = 0;
   size_t g_op, d1_op, d2_op, logits, c_f32, pool_op, scal, pack_tmp;
 
   template <typename T = void>
@@ -184,15 +185,16 @@ static size_t plan(pp_engine* e) {
     e->qkv = b.take((size_t)M * 3 * D * sizeof(float));
     e->h_op = b.take(pp_operand_bytes(prec, M, FF));
   }
-  e->feat_op = b.take(pp_operand_bytes(prec, M, D));
+  // feat_op and d1_op are zero-bordered maps (gh + 2) x (gw + 2) / (2 gh + 2) x (2 gw + 2): the tap
+  // operands of the head's implicit-GEMM deconvolutions / 3x3 convolution (borders zeroed in finalize)
+  const int64_t Mp0 = (int64_t)e->max_b2 * (e->gh + 2) * (e->gw + 2), Mp1 = (int64_t)e->max_b2 * (2 * e->gh + 2) * (2 * e->gw + 2);
+  e->feat_op = b.take(pp_operand_bytes(prec, Mp0, D));
+  e->feat_bytes = pp_operand_bytes(prec, Mp0, D);
   e->feat_f32 = b.take((size_t)M * D * sizeof(float));
   if (DC > 0) {
-    size_t g = pp_operand_bytes(prec, M, 9 * D);
-    const size_t g2 = pp_operand_bytes(prec, 4 * M, 4 * DC), g1 = pp_operand_bytes(prec, M, 4 * D);
-    if (g2 > g) g = g2;
-    if (g1 > g) g = g1;
-    e->g_op = b.take(g);
-    e->d1_op = b.take(pp_operand_bytes(prec, 4 * M, DC));
+    e->g_op = b.take(pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 9 * D));  // tap gather of the pooled 4x4 / 2x2 stages
+    e->d1_op = b.take(pp_operand_bytes(prec, Mp1, DC));
+    e->d1_bytes = pp_operand_bytes(prec, Mp1, DC);
     e->d2_op = b.take(pp_operand_bytes(prec, 16 * M, DC));
     e->logits = b.take((size_t)e->max_b2 * K * 16 * e->tokens * sizeof(float));
     e->c_f32 = b.take((size_t)M * 4 * D * sizeof(float));
@@ -324,7 +326,7 @@ static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int ba
     PP_TRY(gemm(e, g, st));
   }
   PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P("backbone.ln1.weight"), e->P("backbone.ln1.bias"), e->cfg.ln_eps, M, D,
-                          e->at<>(e->feat_op), want_f32 ? e->at<float>(e->feat_f32) : nullptr, st); }));
+                          e->at<>(e->feat_op), want_f32 ? e->at<float>(e->feat_f32) : nullptr, st, e->gh, e->gw); }));
   return PP_OK;
 }
 
@@ -332,26 +334,28 @@ static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int ba
 static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cudaStream_t st) {
   const int D = e->D, DC = e->DC, K = e->K, prec = e->prec;
   const int64_t M = (int64_t)n_img * e->tokens;
-  // --- heatmap branch: two stride-2 deconvs as 4 sub-pixel phase GEMMs each, then the 1x1 conv ---
+  // --- heatmap branch: two stride-2 deconvs as 4 sub-pixel phase GEMMs each, then the 1x1 conv.
+  // Implicit GEMM: the A operand is the zero-bordered input map itself, read at 4 row shifts (taps).
   for (int i = 0; i < 2; ++i) {
     const int cin = i == 0 ? D : DC, h = e->gh << i, w = e->gw << i;
-    const int64_t rows = (int64_t)n_img * h * w;
+    const int64_t rows = (int64_t)n_img * (h + 2) * (w + 2);
     const void* src = i == 0 ? e->at<>(e->feat_op) : e->at<>(e->d1_op);
     void* dst = i == 0 ? e->at<>(e->d1_op) : e->at<>(e->d2_op);
     for (int ph = 0; ph < 4; ++ph) {
       const int py = ph >> 1, px = ph & 1;
-      GatherParams gp = {};
-      gp.batch = n_img; gp.h = h; gp.w = w; gp.c = cin; gp.src_c = cin; gp.c_off = 0; gp.ntaps = 4;
+      pp_gemm_args g = gemm_args(e, rows, DC, 4 * cin, src, e->at<>(e->w_dc[i][ph]));
+      g.a_taps = 4;
       for (int t = 0; t < 4; ++t) {
-        int kk;
-        deconv_tap(py, t >> 1, &gp.dy[t], &kk);
-        deconv_tap(px, t & 1, &gp.dx[t], &kk);
+        int dy, dx, kk;
+        deconv_tap(py, t >> 1, &dy, &kk);
+        deconv_tap(px, t & 1, &dx, &kk);
+        g.a_tap_shift[t] = dy * (w + 2) + dx;
       }
-      PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_gather_taps(prec, gp, src, e->at<>(e->g_op), st); }));
-      pp_gemm_args g = gemm_args(e, rows, DC, 4 * cin, e->at<>(e->g_op), e->at<>(e->w_dc[i][ph]));
       g.scale = e->at<float>(e->dc_scale[i]); g.shift = e->at<float>(e->dc_shift[i]); g.act = PP_ACT_RELU;
       g.out_kind = PP_OUT_OPERAND; g.ldd = DC; g.d = dst;
+      g.in_pad = 1; g.in_h = h; g.in_w = w; g.out_pad = i == 0 ? 1 : 0;
       g.up_hin = h; g.up_win = w; g.up_py = py; g.up_px = px;
+      if (e->profiling) e->prof_gemm_flops -= 2.0 * (rows - (double)n_img * h * w) * DC * 4 * cin;  // border rows are not algorithmic work
       PP_TRY(gemm(e, g, st));
     }
   }
@@ -360,17 +364,22 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
     g.shift = e->P("head.final_layer.bias"); g.out_kind = PP_OUT_PLANES; g.plane = 16 * e->tokens; g.d = logits;
     PP_TRY(gemm(e, g, st));
   }
-  // --- four scalar branches; the first conv of all four shares its input -> one GEMM, N = 4 D ---
+  // --- four scalar branches; the first conv of all four shares its input -> one GEMM, N = 4 D,
+  // 9 taps over the zero-bordered feature map ---
+  {
+    const int64_t rows = (int64_t)n_img * (e->gh + 2) * (e->gw + 2);
+    pp_gemm_args g = gemm_args(e, rows, 4 * D, 9 * D, e->at<>(e->feat_op), e->at<>(e->w_c1));
+    g.a_taps = 9;
+    for (int t = 0; t < 9; ++t) g.a_tap_shift[t] = (t / 3 - 1) * (e->gw + 2) + (t % 3 - 1);
+    g.in_pad = 1; g.in_h = e->gh; g.in_w = e->gw;
+    g.scale = e->at<float>(e->c_scale[0]); g.shift = e->at<float>(e->c_shift[0]); g.d = e->at<>(e->c_f32);
+    if (e->profiling) e->prof_gemm_flops -= 2.0 * (rows - (double)M) * 4 * D * 9 * D;
+    PP_TRY(gemm(e, g, st));
+  }
   GatherParams g3 = {};
   g3.ntaps = 9;
   for (int t = 0; t < 9; ++t) { g3.dy[t] = t / 3 - 1; g3.dx[t] = t % 3 - 1; }
-  g3.batch = n_img; g3.h = e->gh; g3.w = e->gw; g3.c = D; g3.src_c = D; g3.c_off = 0;
-  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_gather_taps(prec, g3, e->at<>(e->feat_op), e->at<>(e->g_op), st); }));
-  {
-    pp_gemm_args g = gemm_args(e, M, 4 * D, 9 * D, e->at<>(e->g_op), e->at<>(e->w_c1));
-    g.scale = e->at<float>(e->c_scale[0]); g.shift = e->at<float>(e->c_shift[0]); g.d = e->at<>(e->c_f32);
-    PP_TRY(gemm(e, g, st));
-  }
+  g3.batch = n_img; g3.c = D;
   int h = e->gh, w = e->gw;
   const int pool[3][2] = {{4, 3}, {2, 2}, {2, 2}};  // probmap_head.py:264
   for (int j = 1; j < 3; ++j) {
@@ -467,6 +476,7 @@ extern "C" int pp_engine_finalize(pp_engine* e, void* stream) {
                "pp_engine_finalize: %d of %d %s parameters loaded; first missing '%s'", loaded[g], total[g],
                g ? "head" : "backbone", missing[g]->name.c_str());
   PP_REQUIRE(loaded[0] + loaded[1] > 0, PP_ERR_STATE, "pp_engine_finalize: no parameters loaded");
+  PP_CHECK_CUDA(cudaMemsetAsync(e->at<>(e->feat_op), 0, e->feat_bytes, st));  // zero border of the padded feature map
   const int D = e->D, FF = e->FF, DC = e->DC, K = e->K;
   if (total[0] > 0 && loaded[0] == total[0]) {
     PP_TRY(to_operand(e, e->P("backbone.patch_embed.projection.weight"), D, e->PK, e->w_patch, st));
@@ -515,6 +525,7 @@ extern "C" int pp_engine_finalize(pp_engine* e, void* stream) {
       PP_TRY(launch_pack_conv3x3(e->P(p + "8.weight"), D, D, tmp, st));
       PP_TRY(to_operand(e, tmp, D, 9 * D, e->w_c3[br], st));
     }
+    PP_CHECK_CUDA(cudaMemsetAsync(e->at<>(e->d1_op), 0, e->d1_bytes, st));
     e->head_ready = true;
   }
   return PP_OK;
@@ -540,7 +551,7 @@ extern "C" int pp_engine_head(pp_engine* e, const float* feat_nchw, int32_t batc
   PP_REQUIRE(batch == 0 || (feat_nchw && heat_logits && scalars), PP_ERR_INVALID, "pp_engine_head: NULL tensor");
   const int64_t before = g_launch_count;
   if (batch > 0) {
-    PP_TRY(launch_nchw_to_operand(e->prec, feat_nchw, batch, e->tokens, e->D, e->at<>(e->feat_op), (cudaStream_t)stream));
+    PP_TRY(launch_nchw_to_operand(e->prec, feat_nchw, batch, e->tokens, e->D, e->at<>(e->feat_op), (cudaStream_t)stream, e->gh, e->gw));
     PP_TRY(run_head(e, batch, heat_logits, scalars, (cudaStream_t)stream));
   }
   e->last_launches = g_launch_count - before;

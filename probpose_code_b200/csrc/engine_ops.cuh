@@ -20,8 +20,9 @@ struct PatchifyParams {
 int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t st);
 
 // Row LayerNorm of fp32 (rows, d) -> operand (rows, d) and, optionally, fp32 (rows, d).
+// pad_gw > 0: operand rows go to the interior of a zero-bordered (pad_gh + 2) x (pad_gw + 2) map per image.
 int launch_layernorm(int prec, const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
-                     void* out_op, float* out_f32, cudaStream_t st);
+                     void* out_op, float* out_f32, cudaStream_t st, int pad_gh = 0, int pad_gw = 0);
 
 // Global multi-head attention on packed qkv fp32 (B * n, 3 * heads * dh) -> operand (B * n, heads * dh).
 int launch_attention(int prec, const float* qkv, int batch, int n, int heads, int dh, void* out_op, cudaStream_t st);
@@ -33,7 +34,8 @@ int launch_attention_mma(int prec, const void* qkv_op, int batch, int n, int hea
 
 // fp32 token rows (B * hw, c) <-> fp32 NCHW (B, c, hw); NCHW -> operand rows.
 int launch_rows_to_nchw(const float* rows, int batch, int hw, int c, float* nchw, cudaStream_t st);
-int launch_nchw_to_operand(int prec, const float* nchw, int batch, int hw, int c, void* rows_op, cudaStream_t st);
+int launch_nchw_to_operand(int prec, const float* nchw, int batch, int hw, int c, void* rows_op, cudaStream_t st,
+                           int pad_gh = 0, int pad_gw = 0);
 
 // ---- head_ops.cu --------------------------------------------------------------------------
 // Tap gather ("im2col" of one tap list) between operands:

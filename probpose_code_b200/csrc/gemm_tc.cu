@@ -70,12 +70,71 @@ struct GemmCfg {
   static_assert(BN % 32 == 0, "epilogue works on 32-column chunks");
 };
 
-__device__ __forceinline__ float4 act4(float4 v, int act) {
-  v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+// erf by Abramowitz & Stegun 7.1.26 (|error| < 6e-7 in fp32, below the rounding noise of an fp32
+// GELU): branch-free, two MUFU ops, so the fc1 epilogue stays well under the tile's MMA time and the
+// kernel stays inside the instruction cache.  (The CUDA-core verification GEMM keeps erff.)
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float x = v * 0.70710678118654752440f;
+  const float a = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(a * a) * 1.4426950408889634f));
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  return 0.5f * v * (1.0f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
 
-template <int BN, int SPLIT, bool BF16>
+// Four consecutive columns of one operand row (col % 4 == 0), see common.cuh "GEMM operand formats";
+// rowk = row * k (element offset of the row in the LOGICAL (rows, k) matrix).
+template <int PREC>
+__device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int col, int k, float4 v) {
+  if constexpr (PREC == PP_PREC_FP16X3) {
+    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((v.x - f0.x) * kLoScale, (v.y - f0.y) * kLoScale);
+    const __half2 l1 = __floats2half2_rn((v.z - f1.x) * kLoScale, (v.w - f1.y) * kLoScale);
+    __half* p = reinterpret_cast<__half*>(base) + 2 * rowk + col;
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(p) = hi;
+    *reinterpret_cast<uint2*>(p + k) = lo;
+  } else if constexpr (PREC == PP_PREC_BF16) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + rowk + col) = o;
+  } else {
+    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + rowk + col) = o;
+  }
+}
+
+template <int BN, int SPLIT, bool BF16, int OUT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const int K,
                const int num_m_tiles, const int num_n_tiles, const TapParams tp, const EpiParams e) {
@@ -187,24 +246,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int ew = warp - 2;
     const int q = warp & 3;     // TMEM lane quarter this warp may access
     const int half = ew >> 2;   // which of the quarter's two warps
-    float4* stg = staging + ew * 256;
+    const uint32_t stg = ptx::smem_u32(staging) + ew * 4096;  // this warp's 32 x 32 fp32 transpose tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int c4 = lane & 7, rsub = lane >> 3;
+    const bool vec_ok = (e.ldd & 3) == 0;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m0 = (tile / num_n_tiles) * kBM, n0 = (tile % num_n_tiles) * BN;
       const int as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       const int row_base = m0 + q * 32;
-      // output rows of the 8 row slots this lane stores (row_base + i * 4 + rsub)
-      int64_t orow[8];
-      uint32_t vmask = 0;
-      if (e.out_kind != PP_OUT_PLANES) {
+      // the 8 row slots this lane stores (row_base + i * 4 + rsub): element offset of the output row
+      // (and of the residual row), or -1 for rows that produce nothing.  One division per tile, then
+      // the map position advances incrementally (4 rows per slot).
+      int64_t doff[8], roff[8];
+      if constexpr (OUT != PP_OUT_PLANES) {
+        const int m_first = row_base + rsub;
+        if (e.up_hin == 0 && e.in_pad == 0 && e.out_pad == 0) {
+          int rm = e.res_mod > 0 ? m_first % e.res_mod : 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          bool ok;
-          orow[i] = map_out_row(e, row_base + i * 4 + rsub, ok);
-          vmask |= ok ? (1u << i) : 0u;
+          for (int i = 0; i < 8; ++i) {
+            const int m = m_first + 4 * i;
+            doff[i] = m < e.m ? (int64_t)m * e.ldd : -1;
+            roff[i] = (int64_t)(e.res_mod > 0 ? rm : m) * e.ldd;
+            rm += 4;
+            while (e.res_mod > 0 && rm >= e.res_mod) rm -= e.res_mod;
+          }
+        } else {
+          const int pad = e.in_pad, op = e.out_pad;
+          const int wp = e.in_w + 2 * pad, hp = e.in_h + 2 * pad;
+          int pj = m_first % wp, t = m_first / wp;
+          int pi = t % hp, pb = t / hp;
+          const int ow = (e.up_hin ? 2 : 1) * e.in_w + 2 * op, oh = (e.up_hin ? 2 : 1) * e.in_h + 2 * op;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = (m_first + 4 * i < e.m) && pj >= pad && pj < e.in_w + pad && pi >= pad && pi < e.in_h + pad;
+            const int ii = pi - pad, jj = pj - pad;
+            const int oy = e.up_hin ? 2 * ii + e.up_py + op : ii + op, ox = e.up_hin ? 2 * jj + e.up_px + op : jj + op;
+            const int64_t orow = (int64_t)(pb * oh + oy) * ow + ox;
+            doff[i] = ok ? orow * e.ldd : -1;
+            roff[i] = orow * e.ldd;
+            pj += 4;
+            while (pj >= wp) { pj -= wp; ++pi; }
+            while (pi >= hp) { pi -= hp; ++pb; }
+          }
         }
       }
       ptx::mbar_wait(&tmem_full_bar[as], aph);
@@ -227,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
         }
         if (n0 + c0 >= e.n) continue;
-        if (e.out_kind == PP_OUT_PLANES) {
+        if constexpr (OUT == PP_OUT_PLANES) {
           // (M / plane, N, plane): lanes are consecutive pixels of one plane -> already coalesced
           const int row = row_base + lane;
           if (row < e.m) {
@@ -238,60 +323,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               const int n = n0 + c0 + c;
               if (n < e.n) {
                 const float sc = e.scale ? __ldg(e.scale + n) : 1.f, sh = e.shift ? __ldg(e.shift + n) : 0.f;
-                dbase[(int64_t)c * e.plane] = apply_act(fmaf(v[c], sc, sh), e.act);
+                float x = fmaf(v[c], sc, sh);
+                if (e.act == PP_ACT_GELU) x = gelu_fast(x);
+                if (e.act == PP_ACT_RELU) x = fmaxf(x, 0.f);
+                dbase[(int64_t)c * e.plane] = x;
               }
             }
           }
-          continue;
+        } else {
+          // transpose through swizzled shared memory: lane (row) writes 8 float4, then each lane
+          // reads float4 column c4 of rows i * 4 + rsub -> 128-byte row segments per 8 lanes
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_f4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          __syncwarp();
+          const int col = n0 + c0 + c4 * 4;
+          if (col + 4 <= e.n && vec_ok) {
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.scale) sc = __ldg(reinterpret_cast<const float4*>(e.scale + col));
+            if (e.shift) sh = __ldg(reinterpret_cast<const float4*>(e.shift + col));
+            float4 x[8], rr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + rsub;
+              x[i] = ld_shared_f4(stg + r * 128 + ((c4 ^ (r & 7)) << 4));
+            }
+            if constexpr (OUT == PP_OUT_F32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.residual != nullptr && doff[i] >= 0) rr[i] = *reinterpret_cast<const float4*>(e.residual + roff[i] + col);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[i].x = fmaf(x[i].x, sc.x, sh.x); x[i].y = fmaf(x[i].y, sc.y, sh.y);
+              x[i].z = fmaf(x[i].z, sc.z, sh.z); x[i].w = fmaf(x[i].w, sc.w, sh.w);
+            }
+            if (e.act == PP_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { x[i].x = gelu_fast(x[i].x); x[i].y = gelu_fast(x[i].y); x[i].z = gelu_fast(x[i].z); x[i].w = gelu_fast(x[i].w); }
+            } else if (e.act == PP_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f); }
+            }
+            if constexpr (OUT == PP_OUT_F32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                x[i].x += rr[i].x; x[i].y += rr[i].y; x[i].z += rr[i].z; x[i].w += rr[i].w;
+                if (doff[i] >= 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.d) + doff[i] + col) = x[i];
+              }
+            } else {  // PP_OUT_OPERAND: doff = row * ldd elements of the logical operand
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (doff[i] >= 0) store_operand4_row<PREC>(e.d, doff[i], col, e.ldd, x[i]);
+            }
+          } else if (col < e.n) {  // ragged right edge or unaligned rows: scalar, rolled
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + rsub;
+              bool ok;
+              const int64_t orow = map_out_row(e, row_base + r, ok);
+              if (!ok) continue;
+              const int64_t rrow = e.res_mod > 0 ? (int)orow % e.res_mod : orow;
+              const uint32_t src = stg + r * 128 + ((c4 ^ (r & 7)) << 4);
+#pragma unroll 1
+              for (int c = 0; c < 4 && col + c < e.n; ++c) {
+                const float sc = e.scale ? __ldg(e.scale + col + c) : 1.f, sh = e.shift ? __ldg(e.shift + col + c) : 0.f;
+                float x = fmaf(ld_shared_f1(src + 4 * c), sc, sh);
+                if (e.act == PP_ACT_GELU) x = gelu_fast(x);
+                if (e.act == PP_ACT_RELU) x = fmaxf(x, 0.f);
+                if constexpr (OUT == PP_OUT_F32) {
+                  if (e.residual) x += e.residual[rrow * e.ldd + col + c];
+                  reinterpret_cast<float*>(e.d)[orow * e.ldd + col + c] = x;
+                } else {
+                  store_operand<PREC>(e.d, orow, col + c, e.ldd, x);
+                }
+              }
+            }
+          }
+          __syncwarp();  // staging tile is rewritten by the next chunk
         }
-        // transpose through swizzled shared memory: lane (row) writes 8 float4, then each lane
-        // reads float4 column c4 of rows i * 4 + rsub -> 128-byte row segments per 8 lanes
-#pragma unroll
-        for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        const int col = n0 + c0 + c4 * 4;
-        if (col + 4 <= e.n && (e.ldd & 3) == 0) {
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.scale) sc = __ldg(reinterpret_cast<const float4*>(e.scale + col));
-          if (e.shift) sh = __ldg(reinterpret_cast<const float4*>(e.shift + col));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!((vmask >> i) & 1u)) continue;
-            const int r = i * 4 + rsub;
-            float4 x = stg[r * 8 + (c4 ^ (r & 7))];
-            x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y); x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
-            x = act4(x, e.act);
-            if (e.out_kind == PP_OUT_F32) {
-              float* dp = reinterpret_cast<float*>(e.d) + orow[i] * e.ldd + col;
-              if (e.residual) {
-                const float4 rr = *reinterpret_cast<const float4*>(e.residual + (e.res_mod > 0 ? orow[i] % e.res_mod : orow[i]) * e.ldd + col);
-                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-              }
-              *reinterpret_cast<float4*>(dp) = x;
-            } else {
-              store_operand4<PREC>(e.d, orow[i], col, e.ldd, x);
-            }
-          }
-        } else if (col < e.n) {  // ragged right edge (n % 4 != 0): scalar
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!((vmask >> i) & 1u)) continue;
-            const int r = i * 4 + rsub;
-            const float4 x4 = stg[r * 8 + (c4 ^ (r & 7))];
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-            for (int c = 0; c < 4 && col + c < e.n; ++c) {
-              const float sc = e.scale ? __ldg(e.scale + col + c) : 1.f, sh = e.shift ? __ldg(e.shift + col + c) : 0.f;
-              float x = apply_act(fmaf(xs[c], sc, sh), e.act);
-              if (e.out_kind == PP_OUT_F32) {
-                if (e.residual) x += e.residual[(e.res_mod > 0 ? orow[i] % e.res_mod : orow[i]) * e.ldd + col + c];
-                reinterpret_cast<float*>(e.d)[orow[i] * e.ldd + col + c] = x;
-              } else {
-                store_operand<PREC>(e.d, orow[i], col + c, e.ldd, x);
-              }
-            }
-          }
-        }
-        __syncwarp();  // staging tile is rewritten by the next chunk
       }
       if (half >= BN / 32) {  // this warp had no chunk (BN == 32): still release the stage
         ptx::tcgen05_fence_before();
@@ -367,11 +479,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int SPLIT, bool BF16>
+template <int BN, int SPLIT, bool BF16, int OUT>
 static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SPLIT>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, SPLIT, BF16>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, BF16, OUT>;
   if (!attr_set) {
     PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
@@ -391,14 +503,27 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams&
   return PP_OK;
 }
 
+template <int BN, int SPLIT, bool BF16>
+static int launch_tc_out(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
+  switch (a.out_kind) {
+    case PP_OUT_F32: return launch_tc<BN, SPLIT, BF16, PP_OUT_F32>(a, e, tp, st);
+    case PP_OUT_OPERAND: return launch_tc<BN, SPLIT, BF16, PP_OUT_OPERAND>(a, e, tp, st);
+    case PP_OUT_PLANES:
+      if constexpr (BN <= 64) return launch_tc<BN, SPLIT, BF16, PP_OUT_PLANES>(a, e, tp, st);
+  }
+  set_error("pp_gemm: out_kind %d not built for tile_n %d", a.out_kind, BN);
+  return PP_ERR_INVALID;
+}
+
 template <int SPLIT, bool BF16>
 static int launch_tc_bn(int bn, const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
+  if (a.out_kind == PP_OUT_PLANES && bn > 64) bn = 64;  // channel-plane output is built for narrow tiles (N = 17 logits)
   switch (bn) {
-    case 32: return launch_tc<32, SPLIT, BF16>(a, e, tp, st);
-    case 64: return launch_tc<64, SPLIT, BF16>(a, e, tp, st);
-    case 128: return launch_tc<128, SPLIT, BF16>(a, e, tp, st);
-    case 192: return launch_tc<192, SPLIT, BF16>(a, e, tp, st);
-    case 256: return launch_tc<256, SPLIT, BF16>(a, e, tp, st);
+    case 32: return launch_tc_out<32, SPLIT, BF16>(a, e, tp, st);
+    case 64: return launch_tc_out<64, SPLIT, BF16>(a, e, tp, st);
+    case 128: return launch_tc_out<128, SPLIT, BF16>(a, e, tp, st);
+    case 192: return launch_tc_out<192, SPLIT, BF16>(a, e, tp, st);
+    case 256: return launch_tc_out<256, SPLIT, BF16>(a, e, tp, st);
   }
   set_error("pp_gemm: unsupported tile_n %d", bn);
   return PP_ERR_INVALID;

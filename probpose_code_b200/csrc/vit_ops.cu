@@ -61,10 +61,19 @@ int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t 
 // ---- LayerNorm ----------------------------------------------------------------------------
 // One warp per row; the row lives in registers (NV float4 per lane, d = 128 * NV).
 // Two-pass mean / variance in fp32 like ATen's CPU and CUDA kernels.
+// pad_gw > 0: the operand output is a zero-bordered (pad_gh + 2) x (pad_gw + 2) map per image (the tap
+// operand of the head's implicit-GEMM convolutions); token (y, x) lands at (y + 1, x + 1).
+__device__ __forceinline__ int64_t padded_row(int64_t row, int gh, int gw) {
+  const int tokens = gh * gw;
+  const int64_t b = row / tokens;
+  const int t = (int)(row % tokens);
+  return (b * (gh + 2) + t / gw + 1) * (gw + 2) + t % gw + 1;
+}
+
 template <int PREC, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int64_t rows,
-                                                        void* out_op, float* out_f32) {
+                                                        void* out_op, float* out_f32, int pad_gh, int pad_gw) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -85,6 +94,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const int64_t op_row = pad_gw > 0 ? padded_row(row, pad_gh, pad_gw) : row;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = (lane + 32 * i) * 4;
@@ -95,20 +105,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (out_op) store_operand4<PREC>(out_op, row, col, D, o);
+    if (out_op) store_operand4<PREC>(out_op, op_row, col, D, o);
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + col) = o;
   }
 }
 
 int launch_layernorm(int prec, const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
-                     void* out_op, float* out_f32, cudaStream_t st) {
+                     void* out_op, float* out_f32, cudaStream_t st, int pad_gh, int pad_gw) {
   PP_REQUIRE(d == 384 || d == 768, PP_ERR_UNSUPPORTED, "LayerNorm width %d not built (384, 768)", d);
   if (rows == 0) return PP_OK;
   const int grid = (int)((rows + 7) / 8);
   if (d == 384) {
-    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 3><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32)));
+    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 3><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32, pad_gh, pad_gw)));
   } else {
-    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 6><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32)));
+    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 6><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32, pad_gh, pad_gw)));
   }
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
@@ -242,7 +252,8 @@ int launch_rows_to_nchw(const float* rows, int batch, int hw, int c, float* nchw
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(256) nchw_to_operand_kernel(const float* __restrict__ nchw, int hw, int c, void* rows_op) {
+__global__ void __launch_bounds__(256) nchw_to_operand_kernel(const float* __restrict__ nchw, int hw, int c, void* rows_op,
+                                                              int pad_gh, int pad_gw) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -250,13 +261,17 @@ __global__ void __launch_bounds__(256) nchw_to_operand_kernel(const float* __res
     if (c0 + r < c && p0 + tx < hw) tile[r][tx] = nchw[((size_t)b * c + c0 + r) * hw + p0 + tx];
   __syncthreads();
   for (int r = ty; r < 32; r += 8)
-    if (p0 + r < hw && c0 + tx < c) store_operand<PREC>(rows_op, (int64_t)b * hw + p0 + r, c0 + tx, c, tile[tx][r]);
+    if (p0 + r < hw && c0 + tx < c) {
+      const int64_t row = (int64_t)b * hw + p0 + r;
+      store_operand<PREC>(rows_op, pad_gw > 0 ? padded_row(row, pad_gh, pad_gw) : row, c0 + tx, c, tile[tx][r]);
+    }
 }
 
-int launch_nchw_to_operand(int prec, const float* nchw, int batch, int hw, int c, void* rows_op, cudaStream_t st) {
+int launch_nchw_to_operand(int prec, const float* nchw, int batch, int hw, int c, void* rows_op, cudaStream_t st, int pad_gh,
+                           int pad_gw) {
   if (batch == 0) return PP_OK;
   dim3 grid((hw + 31) / 32, (c + 31) / 32, batch);
-  PP_DISPATCH_PREC(prec, (nchw_to_operand_kernel<PREC><<<grid, 256, 0, st>>>(nchw, hw, c, rows_op)));
+  PP_DISPATCH_PREC(prec, (nchw_to_operand_kernel<PREC><<<grid, 256, 0, st>>>(nchw, hw, c, rows_op, pad_gh, pad_gw)));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
