@@ -137,6 +137,8 @@ typedef struct pp_gemm_args {
   int32_t a_tap_shift[9];
   int32_t in_pad, in_h, in_w; /* in_h / in_w also required by up_* when in_pad = 1           */
   int32_t out_pad;
+  int32_t cta_pair;       /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pairs (tcgen05
+                             cta_group::2, 256-row tiles) - tuning / tests                   */
 } pp_gemm_args;
 
 PP_API int pp_gemm(const pp_gemm_args* args, void* stream);

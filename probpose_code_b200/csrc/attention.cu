@@ -12,9 +12,9 @@
 //   P = exp2((S - rowmax) * scale * log2 e)                 fp32, row sums by quad shuffles
 //   O = P V     the S accumulator layout IS the A-fragment layout of the second product
 //   out = O / rowsum  -> written as the proj GEMM's A operand
-// In the FP16X3 parity mode every product is the same 3-term split the GEMMs use
-// (hi.hi + 2^-11 (hi.lo' + lo'.hi)), with Q, K, V arriving pre-split from the qkv GEMM epilogue
-// and P split in registers.
+// In the FP16X3 parity mode every product is the same 3-term split the GEMMs use (hi.hi + hi.lo +
+// lo.hi of 64x-scaled operands, one fp32 accumulator), with Q, K, V arriving pre-split from the qkv
+// GEMM epilogue and P split in registers (the factor 64 of P is folded into the exponent).
 //
 // Attention is 7.7 % of the block FLOPs with d_h = 32 (K = 32 per QK^T product) and is bound by the
 // exp / conversion work, not by tensor throughput, so it uses the register-level mma.sync path; the
@@ -66,10 +66,11 @@ __device__ __forceinline__ uint32_t pack2(float x, float y) {
     return *reinterpret_cast<uint32_t*>(&v);
   }
 }
+// x, y are already in operand units (64x the value they stand for)
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x, y);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((x - hf.x) * kLoScale, (y - hf.y) * kLoScale);
+  const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -114,7 +115,9 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
   const uint32_t sV[2] = {s_base + NOPS * ARR, s_base + (NOPS + 1) * ARR};
 
   const int g = lane >> 2, t4 = lane & 3;
-  const float c_exp = rsqrtf((float)DH) * 1.4426950408889634f;  // scale * log2(e)
+  // exp2 argument scale: d_h^-0.5 * log2(e); FP16X3 scores carry the operand scale 64 * 64
+  const float c_exp = rsqrtf((float)DH) * 1.4426950408889634f * (SPLIT == 3 ? kAccScaleInv : 1.0f);
+  const float p_exp = SPLIT == 3 ? 6.0f : 0.0f;  // P leaves the exponential already in operand units (x 2^6)
 
   for (int rt = warp; rt < RT; rt += kAttThreads / 32) {
     // ---- Q fragments (A operand, row-major): rows rt*16 + g (+8), k = ks*16 + 2 t4 (+8) ----
@@ -143,7 +146,7 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
     const uint32_t k_lane = (uint32_t)((lane & 7) * ROWB + (lane >> 3) * 16);
 #pragma unroll
     for (int nt = 0; nt < KT; ++nt) {
-      float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+      float a0[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int kp = 0; kp < KS / 2; ++kp) {  // one ldmatrix.x4 covers two k-steps (32 dh)
         uint32_t kh[4], kl[4];
@@ -154,13 +157,13 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
           const int ks = kp * 2 + u;
           mma16816<BF16>(a0, qh[ks], kh[2 * u], kh[2 * u + 1]);
           if constexpr (SPLIT == 3) {
-            mma16816<BF16>(a1, qh[ks], kl[2 * u], kl[2 * u + 1]);
-            mma16816<BF16>(a1, ql[ks], kh[2 * u], kh[2 * u + 1]);
+            mma16816<BF16>(a0, qh[ks], kl[2 * u], kl[2 * u + 1]);
+            mma16816<BF16>(a0, ql[ks], kh[2 * u], kh[2 * u + 1]);
           }
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) s[nt][i] = SPLIT == 3 ? fmaf(a1[i], kLoScaleInv, a0[i]) : a0[i];
+      for (int i = 0; i < 4; ++i) s[nt][i] = a0[i];
     }
 
     // ---- softmax over the 192 keys (rows g and g + 8 of the tile) ----
@@ -175,8 +178,8 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < KT; ++nt) {
-      s[nt][0] = exp2f((s[nt][0] - mx0) * c_exp); s[nt][1] = exp2f((s[nt][1] - mx0) * c_exp);
-      s[nt][2] = exp2f((s[nt][2] - mx1) * c_exp); s[nt][3] = exp2f((s[nt][3] - mx1) * c_exp);
+      s[nt][0] = exp2f(fmaf(s[nt][0] - mx0, c_exp, p_exp)); s[nt][1] = exp2f(fmaf(s[nt][1] - mx0, c_exp, p_exp));
+      s[nt][2] = exp2f(fmaf(s[nt][2] - mx1, c_exp, p_exp)); s[nt][3] = exp2f(fmaf(s[nt][3] - mx1, c_exp, p_exp));
       l0 += s[nt][0] + s[nt][1];
       l1 += s[nt][2] + s[nt][3];
     }
@@ -184,11 +187,11 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 
     // ---- O = P V ----
-    float o0[DT][4], o1[DT][4];
+    float o0[DT][4];
 #pragma unroll
     for (int dt = 0; dt < DT; ++dt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o0[dt][i] = o1[dt][i] = 0.f;
+      for (int i = 0; i < 4; ++i) o0[dt][i] = 0.f;
     // ldmatrix.trans lane address: matrices {keys 0-7, keys 8-15} x {dh chunk c, c + 1}
     const uint32_t v_lane = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * ROWB + (lane >> 4) * 16);
 #pragma unroll
@@ -215,24 +218,23 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
           const int dt = dp * 2 + u;
           mma16816<BF16>(o0[dt], ph, vh[2 * u], vh[2 * u + 1]);
           if constexpr (SPLIT == 3) {
-            mma16816<BF16>(o1[dt], ph, vl[2 * u], vl[2 * u + 1]);
-            mma16816<BF16>(o1[dt], pl, vh[2 * u], vh[2 * u + 1]);
+            mma16816<BF16>(o0[dt], ph, vl[2 * u], vl[2 * u + 1]);
+            mma16816<BF16>(o0[dt], pl, vh[2 * u], vh[2 * u + 1]);
           }
         }
       }
     }
 
     // ---- normalise and write the proj GEMM's A operand (rows b*NTOK + ..., cols h*DH + ...) ----
+    // FP16X3: O carries 64 (P) * 64 (V) and the row sum carries 64, so O / l is already in operand units
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     const size_t orow0 = (size_t)b * NTOK + rt * 16 + g;
     uint16_t* d0 = out_op + orow0 * (NOPS * D) + h * DH + 2 * t4;
     uint16_t* d1 = d0 + (size_t)8 * (NOPS * D);
 #pragma unroll
     for (int dt = 0; dt < DT; ++dt) {
-      float x0, x1, y0, y1;
+      const float x0 = o0[dt][0] * inv0, x1 = o0[dt][1] * inv0, y0 = o0[dt][2] * inv1, y1 = o0[dt][3] * inv1;
       if constexpr (SPLIT == 3) {
-        x0 = fmaf(o1[dt][0], kLoScaleInv, o0[dt][0]) * inv0; x1 = fmaf(o1[dt][1], kLoScaleInv, o0[dt][1]) * inv0;
-        y0 = fmaf(o1[dt][2], kLoScaleInv, o0[dt][2]) * inv1; y1 = fmaf(o1[dt][3], kLoScaleInv, o0[dt][3]) * inv1;
         uint32_t hi, lo;
         split2(x0, x1, hi, lo);
         *reinterpret_cast<uint32_t*>(d0 + dt * 8) = hi;
@@ -241,7 +243,6 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
         *reinterpret_cast<uint32_t*>(d1 + dt * 8) = hi;
         *reinterpret_cast<uint32_t*>(d1 + D + dt * 8) = lo;
       } else {
-        x0 = o0[dt][0] * inv0; x1 = o0[dt][1] * inv0; y0 = o0[dt][2] * inv1; y1 = o0[dt][3] * inv1;
         *reinterpret_cast<uint32_t*>(d0 + dt * 8) = pack2<BF16>(x0, x1);
         *reinterpret_cast<uint32_t*>(d1 + dt * 8) = pack2<BF16>(y0, y1);
       }

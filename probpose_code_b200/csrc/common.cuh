@@ -65,12 +65,17 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
 
 // ---- GEMM operand formats --------------------------------------------------------------
 // An "operand" is the K-major matrix a tensor-core GEMM reads through TMA.
-//   FP16X3 : fp16 (rows, 2K): [hi | lo * 2^11], hi = rn16(a), lo = rn16((a - hi) * 2048)
+//   FP16X3 : fp16 (rows, 2K): [hi | lo], hi = rn16(64 a), lo = rn16(64 a - hi).  The power-of-two
+//            operand scale keeps lo (about 2^-11 |hi|) a NORMAL fp16 number down to |a| = 2^-9
+//            (below that its absolute error is <= 2^-31, irrelevant), so hi.hi + hi.lo + lo.hi can
+//            be accumulated in ONE fp32 accumulator; products carry 64 * 64 = 2^12, removed
+//            exactly in the epilogue.  |a| saturates at 1023.5.
 //   BF16   : bf16 (rows, K)
 //   FP16   : fp16 (rows, K)
 //   FP32   : fp32 (rows, K)   (CUDA-core verification path)
-constexpr float kLoScale = 2048.0f;
-constexpr float kLoScaleInv = 1.0f / 2048.0f;
+constexpr float kOpScale = 64.0f;             // FP16X3 operand scale
+constexpr float kOpScaleInv = 1.0f / 64.0f;
+constexpr float kAccScaleInv = 1.0f / 4096.0f;  // (A * 64) . (W * 64) -> A . W
 
 __host__ __device__ inline int operand_elem_bytes(int prec) { return prec == PP_PREC_FP32_SIMT ? 4 : 2; }
 __host__ __device__ inline int64_t operand_row_elems(int prec, int64_t k) { return prec == PP_PREC_FP16X3 ? 2 * k : k; }
@@ -84,9 +89,10 @@ template <int PREC>
 __device__ __forceinline__ void store_operand(void* base, int64_t row, int col, int k, float v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
     __half* p = reinterpret_cast<__half*>(base) + row * (2 * (int64_t)k);
+    v *= kOpScale;
     __half hi = sat_half(v);
     p[col] = hi;
-    p[k + col] = sat_half((v - __half2float(hi)) * kLoScale);
+    p[k + col] = __float2half_rn(v - __half2float(hi));
   } else if constexpr (PREC == PP_PREC_BF16) {
     reinterpret_cast<__nv_bfloat16*>(base)[row * (int64_t)k + col] = __float2bfloat16_rn(v);
   } else if constexpr (PREC == PP_PREC_FP16) {
@@ -101,10 +107,11 @@ template <int PREC>
 __device__ __forceinline__ void store_operand4(void* base, int64_t row, int col, int k, float4 v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
     __half* p = reinterpret_cast<__half*>(base) + row * (2 * (int64_t)k);
+    v.x *= kOpScale; v.y *= kOpScale; v.z *= kOpScale; v.w *= kOpScale;
     __half h0 = sat_half(v.x), h1 = sat_half(v.y), h2 = sat_half(v.z), h3 = sat_half(v.w);
     __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
-    __half2 c = __halves2half2(sat_half((v.x - __half2float(h0)) * kLoScale), sat_half((v.y - __half2float(h1)) * kLoScale));
-    __half2 d = __halves2half2(sat_half((v.z - __half2float(h2)) * kLoScale), sat_half((v.w - __half2float(h3)) * kLoScale));
+    __half2 c = __floats2half2_rn(v.x - __half2float(h0), v.y - __half2float(h1));
+    __half2 d = __floats2half2_rn(v.z - __half2float(h2), v.w - __half2float(h3));
     uint2 hi, lo;
     hi.x = *reinterpret_cast<uint32_t*>(&a); hi.y = *reinterpret_cast<uint32_t*>(&b);
     lo.x = *reinterpret_cast<uint32_t*>(&c); lo.y = *reinterpret_cast<uint32_t*>(&d);

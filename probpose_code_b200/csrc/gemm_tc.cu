@@ -14,10 +14,15 @@
 //
 // Precision modes (pp_precision):
 //   FP16 / BF16  one MMA per k-slice.
-//   FP16X3       operands are [hi | lo*2^11] fp16 pairs; three MMAs per k-slice:
-//                acc0 += Ahi.Whi ; acc1 += Ahi.Wlo' + Alo'.Whi ; result = acc0 + acc1 * 2^-11.
+//   FP16X3       operands are [hi | lo] fp16 pairs of the 64x-scaled values (common.cuh); three MMAs
+//                per k-slice into ONE accumulator: acc += Ahi.Whi + Ahi.Wlo + Alo.Whi.
 //                fp16 products are exact in the fp32 accumulator, so this recovers ~2^-22
-//                relative operand precision (fp32-grade) at 1/3 of the fp16 tensor rate.
+//                relative operand precision (fp32-grade) at 1/3 of the fp16 tensor rate; the
+//                2^12 operand scale is removed exactly in the epilogue.
+//
+// Tile width: L2 -> shared-memory traffic per MAC goes as (1/BM + 1/BN), and with hi + lo planes the
+// 128 x 128 tile is bound by the ~6 KB/clk L2 fabric at ~47 % tensor activity (measured); the single
+// accumulator lets FP16X3 run 128 x 192 / 128 x 256 tiles with both TMEM stages (2 x 256 columns).
 #include <cuda.h>
 
 #include <map>
@@ -31,7 +36,6 @@
 namespace pp {
 
 constexpr int kBM = 128;
-constexpr int kBK = 64;  // 64 x 16-bit = 128 bytes = one swizzle row
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
 constexpr int kStagingBytes = kEpiWarps * 4096;    // one 32 x 32 fp32 transpose tile per epilogue warp
@@ -48,13 +52,25 @@ struct TapParams {
   int shift[kMaxTaps];
 };
 
-template <int BN, int SPLIT>
+// ACCS (FP16X3 only): 1 = all three products accumulate into one TMEM accumulator (wide tiles keep
+// both TMEM stages); 2 = the cross terms hi.lo + lo.hi go to a second accumulator, so the big
+// accumulator is rounded once per k-slice instead of three times (used for long K, see pick_config).
+// PAIR: two CTAs of a cluster (one TPC) form one 256 x BN tile with tcgen05 cta_group::2: each CTA
+// stages its own 128 A rows and HALF of the W rows, the leader issues M = 256 MMAs that read both
+// shared memories, and each CTA's TMEM receives its 128 accumulator rows.  Per CTA this halves the W
+// bytes pulled from L2 and read from shared memory - the two limits a 128-row tile runs into first
+// (measured: 47 % tensor activity for 128 x 128 FP16X3 tiles, L2 -> SM traffic at 10 TB/s).
+template <int BN, int SPLIT, int ACCS = 1, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;
-  static constexpr int A_BYTES = kBM * kBK * 2;
-  static constexpr int B_BYTES = BN * kBK * 2;
+  // k-block: 64 x 16-bit = one 128-byte swizzle row; wide FP16X3 tiles use 32 (64-byte swizzle rows)
+  // so that four stages of A hi/lo + W hi/lo still fit beside the epilogue staging tiles
+  static constexpr int BK = (SPLIT == 3 && BN > 128 && !PAIR) ? 32 : 64;
+  static constexpr int BN_CTA = PAIR ? BN / 2 : BN;  // W rows this CTA stages
+  static constexpr int NOPS = (SPLIT == 3) ? 2 : 1;  // operand planes (hi, lo)
+  static constexpr int A_BYTES = kBM * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
-  static constexpr int ACC_COLS = NOPS * BN;
+  static constexpr int ACC_COLS = ACCS * BN;
   static constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_NEED = ACC_STAGES * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
@@ -68,6 +84,8 @@ struct GemmCfg {
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert((2 * STAGES + 4) * 8 + 16 <= MISC_BYTES, "barrier block too small");
   static_assert(BN % 32 == 0, "epilogue works on 32-column chunks");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep the swizzle alignment");
+  static_assert(!PAIR || BN % 32 == 0, "pair tiles split W in two halves of whole 16-row groups");
 };
 
 // erf by Abramowitz & Stegun 7.1.26 (|error| < 6e-7 in fp32, below the rounding noise of an fp32
@@ -107,12 +125,12 @@ __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
 template <int PREC>
 __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int col, int k, float4 v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
-    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
-    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+    v.x = fminf(fmaxf(v.x * kOpScale, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y * kOpScale, -65504.f), 65504.f);
+    v.z = fminf(fmaxf(v.z * kOpScale, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w * kOpScale, -65504.f), 65504.f);
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-    const __half2 l0 = __floats2half2_rn((v.x - f0.x) * kLoScale, (v.y - f0.y) * kLoScale);
-    const __half2 l1 = __floats2half2_rn((v.z - f1.x) * kLoScale, (v.w - f1.y) * kLoScale);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y);
+    const __half2 l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
     __half* p = reinterpret_cast<__half*>(base) + 2 * rowk + col;
     uint2 hi, lo;
     hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -134,11 +152,14 @@ __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int
   }
 }
 
-template <int BN, int SPLIT, bool BF16, int OUT>
+// num_m_tiles counts 128-row tiles (PAIR: 256-row pair tiles); gridDim.x CTAs (PAIR: an even number,
+// launched as clusters of 2) walk them persistently.
+template <int BN, int SPLIT, bool BF16, int OUT, int ACCS, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const int K,
                const int num_m_tiles, const int num_n_tiles, const TapParams tp, const EpiParams e) {
-  using Cfg = GemmCfg<BN, SPLIT>;
+  using Cfg = GemmCfg<BN, SPLIT, ACCS, PAIR>;
+  static_assert(ACCS == 1 || SPLIT == 3, "a second accumulator only exists in the split mode");
   constexpr int PREC = SPLIT == 3 ? PP_PREC_FP16X3 : (BF16 ? PP_PREC_BF16 : PP_PREC_FP16);
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -155,9 +176,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   auto stage_a = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + part * Cfg::A_BYTES; };
   auto stage_b = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::A_BYTES + part * Cfg::B_BYTES; };
 
+  constexpr int BK = Cfg::BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = K / kBK;
+  const int num_kb = K / BK;
   const int num_tiles = num_m_tiles * num_n_tiles;
+  // work-unit walk: a CTA (or a CTA pair) starts at its index and strides by the number of units
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = PAIR ? 2 * kBM : kBM;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a);
@@ -168,80 +195,110 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full_bar[s], 1);
-      ptx::mbar_init(&tmem_empty_bar[s], kEpiWarps);
+      ptx::mbar_init(&tmem_empty_bar[s], PAIR ? 2 * kEpiWarps : kEpiWarps);  // the leader collects both CTAs' epilogues
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_2cta(tmem_ptr, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync(); else __syncthreads();  // barriers + TMEM visible (pair: in both CTAs)
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const int kb_per_tap = tp.tap_k / kBK;
+      const int kb_per_tap = tp.tap_k / BK;
       const int a_lo = tp.tap_k;  // column of the lo plane inside an FP16X3 A row
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * kBM, n0 = (tile % num_n_tiles) * BN;
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+        const int m0 = (tile / num_n_tiles) * TILE_M + (int)cta_rank * kBM;
+        const int n0 = (tile % num_n_tiles) * BN + (int)cta_rank * Cfg::BN_CTA;  // pair: this CTA's half of the W tile
         int tap = 0, kc = 0;  // current tap and its k-block
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           const int arow = m0 + tp.shift[tap];
-          ptx::tma_load_2d(stage_a(s, 0), &tm_a, &full_bar[s], kc * kBK, arow);
-          ptx::tma_load_2d(stage_b(s, 0), &tm_w, &full_bar[s], kb * kBK, n0);
-          if constexpr (SPLIT == 3) {
-            ptx::tma_load_2d(stage_a(s, 1), &tm_a, &full_bar[s], a_lo + kc * kBK, arow);
-            ptx::tma_load_2d(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * kBK, n0);
+          if constexpr (PAIR) {
+            // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+            ptx::tma_load_2d_2cta(stage_a(s, 0), &tm_a, &full_bar[s], kc * BK, arow);
+            ptx::tma_load_2d_2cta(stage_b(s, 0), &tm_w, &full_bar[s], kb * BK, n0);
+            if constexpr (SPLIT == 3) {
+              ptx::tma_load_2d_2cta(stage_a(s, 1), &tm_a, &full_bar[s], a_lo + kc * BK, arow);
+              ptx::tma_load_2d_2cta(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * BK, n0);
+            }
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            ptx::tma_load_2d(stage_a(s, 0), &tm_a, &full_bar[s], kc * BK, arow);
+            ptx::tma_load_2d(stage_b(s, 0), &tm_w, &full_bar[s], kb * BK, n0);
+            if constexpr (SPLIT == 3) {
+              ptx::tma_load_2d(stage_a(s, 1), &tm_a, &full_bar[s], a_lo + kc * BK, arow);
+              ptx::tma_load_2d(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * BK, n0);
+            }
           }
           if (++kc == kb_per_tap) { kc = 0; ++tap; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, kBM, BN);
-      uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const int as = lt % ACC_STAGES;
-        const uint32_t aph = (lt / ACC_STAGES) & 1;
-        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);  // epilogue has drained this accumulator stage
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===== MMA issuer: the whole warp walks the pipeline (warp-uniform control flow keeps the
+    // descriptors in uniform registers); one elected lane issues the MMAs and commits.
+    // Pair mode: only the leader CTA issues (M = 256 across both CTAs) =====
+    constexpr uint32_t idesc = ptx::make_idesc_f16(BF16, TILE_M, BN);
+    constexpr uint32_t A_STEP = Cfg::A_BYTES >> 4, B_STEP = Cfg::B_BYTES >> 4;  // plane strides, 16-byte units
+    const uint32_t desc_lo0 = ptx::kmajor_desc_lo(ptx::smem_u32(smem));
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
+      if constexpr (PAIR) ptx::umma_f16_2cta(d, da, db, idesc, accumulate); else ptx::umma_f16(d, da, db, idesc, accumulate);
+    };
+    auto commit = [&](uint64_t* bar) {  // pair: the arrival lands in both CTAs
+      if constexpr (PAIR) ptx::umma_commit_2cta(bar); else ptx::umma_commit(bar);
+    };
+    uint32_t it = 0, lt = 0;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++lt) {
+      const int as = lt % ACC_STAGES;
+      const uint32_t aph = (lt / ACC_STAGES) & 1;
+      ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);  // epilogue has drained this accumulator stage
+      ptx::tcgen05_fence_after();
+      const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
+      const uint32_t acc1 = acc0 + (ACCS == 2 ? BN : 0);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
         ptx::tcgen05_fence_after();
-        const uint32_t acc0 = tmem_base + as * Cfg::ACC_COLS;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tcgen05_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(stage_a(s, 0)), b_hi = ptx::smem_u32(stage_b(s, 0));
+        if (ptx::elect_one()) {
+          const uint32_t a_hi = desc_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+          const uint32_t b_hi = a_hi + Cfg::NOPS * A_STEP;
 #pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk) {
+          for (int kk = 0; kk < BK / 16; ++kk) {
             const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-            const uint64_t da = ptx::make_sw128_kmajor_desc(a_hi + kk * 32);
-            const uint64_t db = ptx::make_sw128_kmajor_desc(b_hi + kk * 32);
-            ptx::umma_f16(acc0, da, db, idesc, acc);
+            const uint64_t da = ptx::kmajor_desc<BK * 2>(a_hi + 2 * kk);
+            const uint64_t db = ptx::kmajor_desc<BK * 2>(b_hi + 2 * kk);
+            mma(acc0, da, db, acc);
             if constexpr (SPLIT == 3) {
-              const uint64_t da_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(stage_a(s, 1)) + kk * 32);
-              const uint64_t db_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(stage_b(s, 1)) + kk * 32);
-              ptx::umma_f16(acc0 + BN, da, db_lo, idesc, acc);
-              ptx::umma_f16(acc0 + BN, da_lo, db, idesc, 1u);
+              const uint64_t da_lo = ptx::kmajor_desc<BK * 2>(a_hi + A_STEP + 2 * kk);
+              const uint64_t db_lo = ptx::kmajor_desc<BK * 2>(b_hi + B_STEP + 2 * kk);
+              mma(acc1, da, db_lo, ACCS == 2 ? acc : 1u);
+              mma(acc1, da_lo, db, 1u);
             }
           }
-          ptx::umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+          commit(&empty_bar[s]);                                // slot reusable once these MMAs have read it
+          if (kb == num_kb - 1) commit(&tmem_full_bar[as]);     // accumulator stage complete
         }
-        ptx::umma_commit(&tmem_full_bar[as]);  // accumulator stage complete
+        __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===== epilogue (8 warps): two warps share a TMEM lane quarter and split its column chunks =====
     const int ew = warp - 2;
     const int q = warp & 3;     // TMEM lane quarter this warp may access
@@ -250,9 +307,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int c4 = lane & 7, rsub = lane >> 3;
     const bool vec_ok = (e.ldd & 3) == 0;
+    constexpr float acc_scale = SPLIT == 3 ? kAccScaleInv : 1.0f;  // FP16X3 operands carry 64 x 64
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int m0 = (tile / num_n_tiles) * kBM, n0 = (tile % num_n_tiles) * BN;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++lt) {
+      const int m0 = (tile / num_n_tiles) * TILE_M + (int)cta_rank * kBM, n0 = (tile % num_n_tiles) * BN;
       const int as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       const int row_base = m0 + q * 32;
@@ -300,16 +358,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int c0 = ch * 32;
         float v[32];
         ptx::tmem_ld_32x32b_x32(tacc + c0, v);
-        if constexpr (SPLIT == 3) {
+        if constexpr (ACCS == 2) {
           float w[32];
           ptx::tmem_ld_32x32b_x32(tacc + BN + c0, w);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(w[i], kLoScaleInv, v[i]);
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
         }
         if (ch + 2 >= BN / 32) {  // last TMEM read of this tile: hand the accumulator stage back
           ptx::tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+          if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]); else ptx::mbar_arrive(&tmem_empty_bar[as]); }
         }
         if (n0 + c0 >= e.n) continue;
         if constexpr (OUT == PP_OUT_PLANES) {
@@ -322,7 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int c = 0; c < 32; ++c) {
               const int n = n0 + c0 + c;
               if (n < e.n) {
-                const float sc = e.scale ? __ldg(e.scale + n) : 1.f, sh = e.shift ? __ldg(e.shift + n) : 0.f;
+                const float sc = (e.scale ? __ldg(e.scale + n) : 1.f) * acc_scale, sh = e.shift ? __ldg(e.shift + n) : 0.f;
                 float x = fmaf(v[c], sc, sh);
                 if (e.act == PP_ACT_GELU) x = gelu_fast(x);
                 if (e.act == PP_ACT_RELU) x = fmaxf(x, 0.f);
@@ -342,6 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e.scale) sc = __ldg(reinterpret_cast<const float4*>(e.scale + col));
             if (e.shift) sh = __ldg(reinterpret_cast<const float4*>(e.shift + col));
+            sc.x *= acc_scale; sc.y *= acc_scale; sc.z *= acc_scale; sc.w *= acc_scale;
             float4 x[8], rr[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -389,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               const uint32_t src = stg + r * 128 + ((c4 ^ (r & 7)) << 4);
 #pragma unroll 1
               for (int c = 0; c < 4 && col + c < e.n; ++c) {
-                const float sc = e.scale ? __ldg(e.scale + col + c) : 1.f, sh = e.shift ? __ldg(e.shift + col + c) : 0.f;
+                const float sc = (e.scale ? __ldg(e.scale + col + c) : 1.f) * acc_scale, sh = e.shift ? __ldg(e.shift + col + c) : 0.f;
                 float x = fmaf(ld_shared_f1(src + 4 * c), sc, sh);
                 if (e.act == PP_ACT_GELU) x = gelu_fast(x);
                 if (e.act == PP_ACT_RELU) x = fmaxf(x, 0.f);
@@ -408,16 +467,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       if (half >= BN / 32) {  // this warp had no chunk (BN == 32): still release the stage
         ptx::tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]); else ptx::mbar_arrive(&tmem_empty_bar[as]); }
       }
     }
   }
 
-  __syncthreads();
+  // pair: neither CTA may leave while the other can still signal its barriers or read its operands
+  ptx::tcgen05_fence_before();
+  if constexpr (PAIR) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) ptx::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -440,12 +501,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// K-major 16-bit operand (rows x row_elems), box = 64 elements x box_rows, 128-byte swizzle, OOB -> 0.
-static int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t row_elems, int box_rows, bool bf16) {
-  typedef std::tuple<const void*, int64_t, int64_t, int, bool> Key;
+// K-major 16-bit operand (rows x row_elems), box = box_cols (64 / 32) elements x box_rows,
+// 128- / 64-byte swizzle, OOB -> 0.
+static int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t row_elems, int box_rows, int box_cols,
+                            bool bf16) {
+  typedef std::tuple<const void*, int64_t, int64_t, int, int, bool> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  const Key key(base, rows, row_elems, box_rows, bf16);
+  const Key key(base, rows, row_elems, box_rows, box_cols, bf16);
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -456,11 +519,12 @@ static int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, in
   PP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, PP_ERR_INVALID, "GEMM operand %p not 16-byte aligned", base);
   const cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)row_elems * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PP_REQUIRE(r == CUDA_SUCCESS, PP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld elems=%lld box_rows=%d", (int)r,
              (long long)rows, (long long)row_elems, box_rows);
   std::lock_guard<std::mutex> lk(mu);
@@ -479,66 +543,101 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int SPLIT, bool BF16, int OUT>
+template <int BN, int SPLIT, bool BF16, int OUT, int ACCS, bool PAIR>
 static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, SPLIT>;
+  using Cfg = GemmCfg<BN, SPLIT, ACCS, PAIR>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, SPLIT, BF16, OUT>;
+  auto kern = gemm_tc_kernel<BN, SPLIT, BF16, OUT, ACCS, PAIR>;
   if (!attr_set) {
     PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int nops = SPLIT == 3 ? 2 : 1;
   CUtensorMap tma, tmw;
-  int rc = make_operand_map(&tma, a.a, a.m, (int64_t)nops * tp.tap_k, kBM, BF16);
+  int rc = make_operand_map(&tma, a.a, a.m, (int64_t)nops * tp.tap_k, kBM, Cfg::BK, BF16);
   if (rc) return rc;
-  rc = make_operand_map(&tmw, a.w, a.n, (int64_t)nops * a.k, BN, BF16);
+  rc = make_operand_map(&tmw, a.w, a.n, (int64_t)nops * a.k, Cfg::BN_CTA, Cfg::BK, BF16);
   if (rc) return rc;
-  const int mt = (a.m + kBM - 1) / kBM, nt = (a.n + BN - 1) / BN;
+  constexpr int TILE_M = PAIR ? 2 * kBM : kBM;
+  const int mt = (a.m + TILE_M - 1) / TILE_M, nt = (a.n + BN - 1) / BN;
   const int64_t tiles = (int64_t)mt * nt;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tma, tmw, a.k, mt, nt, tp, e);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {  // one cluster of 2 CTAs (one TPC) per 256-row tile, as many clusters as fit the SMs
+    const int64_t pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
+  }
+  const int k = a.k;
+  PP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tma, tmw, k, mt, nt, tp, e));
   count_launch();
-  PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
 }
 
-template <int BN, int SPLIT, bool BF16>
+template <int BN, int SPLIT, bool BF16, int ACCS, bool PAIR>
 static int launch_tc_out(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
   switch (a.out_kind) {
-    case PP_OUT_F32: return launch_tc<BN, SPLIT, BF16, PP_OUT_F32>(a, e, tp, st);
-    case PP_OUT_OPERAND: return launch_tc<BN, SPLIT, BF16, PP_OUT_OPERAND>(a, e, tp, st);
+    case PP_OUT_F32: return launch_tc<BN, SPLIT, BF16, PP_OUT_F32, ACCS, PAIR>(a, e, tp, st);
+    case PP_OUT_OPERAND: return launch_tc<BN, SPLIT, BF16, PP_OUT_OPERAND, ACCS, PAIR>(a, e, tp, st);
     case PP_OUT_PLANES:
-      if constexpr (BN <= 64) return launch_tc<BN, SPLIT, BF16, PP_OUT_PLANES>(a, e, tp, st);
+      if constexpr (BN <= 64 && !PAIR) return launch_tc<BN, SPLIT, BF16, PP_OUT_PLANES, ACCS, false>(a, e, tp, st);
   }
   set_error("pp_gemm: out_kind %d not built for tile_n %d", a.out_kind, BN);
   return PP_ERR_INVALID;
 }
 
 template <int SPLIT, bool BF16>
-static int launch_tc_bn(int bn, const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
+static int launch_tc_bn(int bn, int accs, bool pair, const pp_gemm_args& a, const EpiParams& e, const TapParams& tp,
+                        cudaStream_t st) {
   if (a.out_kind == PP_OUT_PLANES && bn > 64) bn = 64;  // channel-plane output is built for narrow tiles (N = 17 logits)
+  if (bn < 128 || a.out_kind == PP_OUT_PLANES) pair = false;  // CTA pairs are built for the wide tiles
+  if constexpr (SPLIT == 3) {
+    if (accs == 2) {  // two accumulators: 2 x BN columns per TMEM stage, so at most 128 wide
+      switch (bn) {
+        case 32: return launch_tc_out<32, SPLIT, BF16, 2, false>(a, e, tp, st);
+        case 64: return launch_tc_out<64, SPLIT, BF16, 2, false>(a, e, tp, st);
+        case 128: return pair ? launch_tc_out<128, SPLIT, BF16, 2, true>(a, e, tp, st)
+                              : launch_tc_out<128, SPLIT, BF16, 2, false>(a, e, tp, st);
+      }
+    }
+  }
   switch (bn) {
-    case 32: return launch_tc_out<32, SPLIT, BF16>(a, e, tp, st);
-    case 64: return launch_tc_out<64, SPLIT, BF16>(a, e, tp, st);
-    case 128: return launch_tc_out<128, SPLIT, BF16>(a, e, tp, st);
-    case 192: return launch_tc_out<192, SPLIT, BF16>(a, e, tp, st);
-    case 256: return launch_tc_out<256, SPLIT, BF16>(a, e, tp, st);
+    case 32: return launch_tc_out<32, SPLIT, BF16, 1, false>(a, e, tp, st);
+    case 64: return launch_tc_out<64, SPLIT, BF16, 1, false>(a, e, tp, st);
+    case 128: return pair ? launch_tc_out<128, SPLIT, BF16, 1, true>(a, e, tp, st) : launch_tc_out<128, SPLIT, BF16, 1, false>(a, e, tp, st);
+    case 192: return pair ? launch_tc_out<192, SPLIT, BF16, 1, true>(a, e, tp, st) : launch_tc_out<192, SPLIT, BF16, 1, false>(a, e, tp, st);
+    case 256: return pair ? launch_tc_out<256, SPLIT, BF16, 1, true>(a, e, tp, st) : launch_tc_out<256, SPLIT, BF16, 1, false>(a, e, tp, st);
   }
   set_error("pp_gemm: unsupported tile_n %d", bn);
   return PP_ERR_INVALID;
 }
 
-static int pick_tile_n(int n, int prec) {
+// FP16X3 long-K GEMMs (fc2, deconv phases, 3x3 convolutions) keep the cross terms in a second
+// accumulator: the fp32 accumulator is rounded once per MMA, and K / 16 x 3 roundings of one big
+// accumulator is the dominant error term beyond K ~ 768 (measured: 1.7e-6 relative at K = 384,
+// 1.3e-5 at K = 3456 with one accumulator).  They are MMA-bound at 128-wide tiles anyway.
+constexpr int kTwoAccMinK = 768;
+
+static int pick_tile_n(int n, int k, int prec) {
   if (n <= 32) return 32;
   if (n <= 64) return 64;
-  if (prec == PP_PREC_FP16X3) return 128;  // 2 accumulators x 128 columns x 2 TMEM stages = 512 columns
+  if (prec == PP_PREC_FP16X3 && k > kTwoAccMinK) return 128;
+  // widest tile that divides n: less L2 -> shared-memory traffic per MAC (see the header comment)
   if (n % 256 == 0) return 256;
   if (n % 192 == 0) return 192;
   return 128;
 }
 
 int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaStream_t st) {
+  constexpr int kBK = 64;
   PP_REQUIRE(a.k % kBK == 0 && a.k > 0, PP_ERR_INVALID, "pp_gemm: k=%d must be a positive multiple of %d", a.k, kBK);
   TapParams tp = {};
   tp.taps = a.a_taps > 1 ? a.a_taps : 1;
@@ -546,11 +645,14 @@ int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaSt
              "pp_gemm: %d taps need k=%d to split into multiples of %d", tp.taps, a.k, kBK);
   tp.tap_k = a.k / tp.taps;
   for (int t = 0; t < tp.taps; ++t) tp.shift[t] = a.a_taps > 1 ? a.a_tap_shift[t] : 0;
-  const int bn = tile_n > 0 ? tile_n : pick_tile_n(a.n, a.precision);
+  const int bn = tile_n > 0 ? tile_n : pick_tile_n(a.n, a.k, a.precision);
+  const int accs = (a.precision == PP_PREC_FP16X3 && a.k > kTwoAccMinK && bn <= 128) ? 2 : 1;
+  // CTA pairs pay off once there are enough 256-row tiles to occupy the 74 TPCs
+  const bool pair = a.cta_pair == 2 || (a.cta_pair == 0 && (int64_t)((a.m + 255) / 256) * ((a.n + bn - 1) / bn) >= num_sms() / 2);
   switch (a.precision) {
-    case PP_PREC_FP16X3: return launch_tc_bn<3, false>(bn, a, e, tp, st);
-    case PP_PREC_BF16: return launch_tc_bn<1, true>(bn, a, e, tp, st);
-    case PP_PREC_FP16: return launch_tc_bn<1, false>(bn, a, e, tp, st);
+    case PP_PREC_FP16X3: return launch_tc_bn<3, false>(bn, accs, pair, a, e, tp, st);
+    case PP_PREC_BF16: return launch_tc_bn<1, true>(bn, accs, pair, a, e, tp, st);
+    case PP_PREC_FP16: return launch_tc_bn<1, false>(bn, accs, pair, a, e, tp, st);
   }
   set_error("pp_gemm: precision %d is not a tensor-core mode", a.precision);
   return PP_ERR_INVALID;

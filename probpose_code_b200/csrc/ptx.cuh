@@ -127,19 +127,74 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ---------------------------------------------
+// A shared::cta address is also a valid shared::cluster address of the executing CTA; inside a CTA
+// pair bit 24 selects the CTA, so clearing it names the same offset in the even ("leader") CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// 2-D tiled load into THIS CTA's shared memory whose completion bytes are credited to the barrier at
+// the same offset in the pair's leader CTA (the only CTA that waits for operands: it issues the MMAs).
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N rows: N/2 per CTA]; issued by the leader.
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed.
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// Arrive on the barrier at this offset in the pair's leader CTA (from either CTA).
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------
-// Shared-memory matrix descriptor for a K-major tile stored as rows of 128 bytes with the
-// 128-byte swizzle (what TMA SWIZZLE_128B writes): 8-row groups 1024 B apart.
+// Shared-memory matrix descriptor for a K-major tile stored as rows of ROW_BYTES (128 or 64) with
+// the matching TMA swizzle (SWIZZLE_128B / SWIZZLE_64B): 8-row groups 8 * ROW_BYTES apart.
 //   [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4
-//   [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3fff);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+//   [46,48) version = 1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+// The low word is the only part that changes while walking a tile ring (shared memory is < 256 KB,
+// so start >> 4 never carries out of its 14 bits): lo(addr + d) = lo(addr) + (d >> 4).
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr_bytes) {
+  return ((smem_addr_bytes >> 4) & 0x3fffu) | (1u << 16);
+}
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t lo) {
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle row");
+  constexpr uint32_t hi = (uint32_t)((8 * ROW_BYTES) >> 4) | (1u << 14) | ((ROW_BYTES == 128 ? 2u : 4u) << 29);
+  return ((uint64_t)hi << 32) | lo;
 }
 
 // Instruction descriptor, kind::f16, fp32 accumulate, both operands K-major.

@@ -24,7 +24,7 @@ def _operand_to_f64(buf, rows, k, prec):
     if prec == _lib.PREC_FP16:
         return buf.view(torch.float16).view(rows, k).double()
     h = buf.view(torch.float16).view(rows, 2 * k).double()
-    return h[:, :k] + h[:, k:] / 2048.0
+    return (h[:, :k] + h[:, k:]) / 64.0  # FP16X3: hi + lo of the 64x-scaled value
 
 
 def _rel(a, ref):
@@ -176,3 +176,27 @@ def test_tap_gemm_deconv_phases(prec, out_pad):
     assert _rel(inner, ref) <= TOL[prec] * 4
     if out_pad:
         assert v[:, 0].abs().max() == 0 and v[:, -1].abs().max() == 0 and v[:, :, 0].abs().max() == 0 and v[:, :, -1].abs().max() == 0
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_BF16])
+@pytest.mark.parametrize("m,n,k,tile_n", [(512, 384, 384, 128), (1000, 1152, 384, 192), (2048, 1536, 384, 256),
+                                          (300, 384, 1536, 128), (4096, 256, 1024, 256), (257, 768, 128, 192)])
+def test_cta_pair_gemm(prec, m, n, k, tile_n):
+    """tcgen05 cta_group::2: two CTAs share one 256-row tile (each stages half of W); forced with
+    cta_pair=2 so that small shapes exercise it too, incl. ragged M (TMA zero fill + row masks)."""
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) * 0.05
+    shift = torch.randn(n, device="cuda", generator=g)
+    res = torch.randn(m, n, device="cuda", generator=g)
+    ops = _ops()
+    ao, wo = ops.to_operand(a, prec), ops.to_operand(w, prec)
+    ref = a.double() @ w.double().t() + shift.double()
+    out = ops.gemm(ao, wo, m, n, k, prec, shift=shift, tile_n=tile_n, cta_pair=2)
+    assert _rel(out, ref) <= TOL[prec] * 2
+    single = ops.gemm(ao, wo, m, n, k, prec, shift=shift, tile_n=tile_n, cta_pair=1)
+    assert _rel(out, single.double()) <= 1e-6  # same arithmetic, different tiling of M
+    out = ops.gemm(ao, wo, m, n, k, prec, shift=shift, residual=res, out=res.clone(), tile_n=tile_n, cta_pair=2)
+    assert _rel(out, ref + res.double()) <= TOL[prec] * 2
+    nxt = ops.gemm(ao, wo, m, n, k, prec, shift=shift, act=_lib.ACT_RELU, out_kind=_lib.OUT_OPERAND, tile_n=tile_n, cta_pair=2)
+    assert _rel(_operand_to_f64(nxt, m, n, prec), torch.relu(ref)) <= max(TOL[prec] * 2, {0: 3e-6, 1: 8e-3}[prec])

@@ -90,14 +90,15 @@ def bench_gemm():
             for tile_n in (128, 192, 256):
                 if n % tile_n and n > tile_n:
                     continue
-                try:
-                    med, best = time_ms(lambda: ops.gemm(ao, wo, m, n, k, prec, out=out, tile_n=tile_n), iters=10)
-                except Exception as e:  # noqa: BLE001
-                    emit(dict(kernel="gemm", prec=prec_name, shape=name, tile_n=tile_n, error=str(e)))
-                    continue
-                fl = 2.0 * m * n * k
-                emit(dict(kernel="gemm", prec=prec_name, shape=name, m=m, n=n, k=k, tile_n=tile_n, ms_median=med,
-                          ms_best=best, tflops=fl / med / 1e9, frac_bf16_peak=fl / med / 1e9 / TF))
+                for pair in (1, 2):
+                    try:
+                        med, best = time_ms(lambda: ops.gemm(ao, wo, m, n, k, prec, out=out, tile_n=tile_n, cta_pair=pair), iters=10)
+                    except Exception as e:  # noqa: BLE001
+                        emit(dict(kernel="gemm", prec=prec_name, shape=name, tile_n=tile_n, pair=pair, error=str(e)))
+                        continue
+                    fl = 2.0 * m * n * k
+                    emit(dict(kernel="gemm", prec=prec_name, shape=name, m=m, n=n, k=k, tile_n=tile_n, pair=pair, ms_median=med,
+                              ms_best=best, tflops=fl / med / 1e9, frac_bf16_peak=fl / med / 1e9 / TF))
             del ao, wo, out
 
 
