@@ -1,18 +1,30 @@
-// Fused ProbMap decode for sm_100a: one CTA per (person, keypoint) heatmap.
+// Fused ProbMap decode for sm_100a.
 //
 //   logits (pass, flipped pass) --/T--> sparsemax --*normalize, clamp[0,1]--> P, Pf
 //   merged = 0.5 * (P + mirror(Pf[flip_idx[k]]))                (flip-TTA)
-//   C = merged (*) OKS-Gaussian_k, separable, reflect border     (only over the support's
-//                                                                 dilated bounding box)
+//   C = merged (*) OKS-Gaussian_k, separable, reflect border
 //   (y*, x*) = first arg max C ; one quadratic sub-pixel step on C ; conf = merged[y*, x*]
 //   record = [x, y, conf, prob, vis, oks, err / diag]
 //
 // Reference semantics: probmap_head.py:641-645,757-798, tta.py:35-39,
 // post_processing.py:13-39,308-430 (see include/probpose_b200.h: pp_decode).
 //
-// The kernel is HBM-bound by design: each map (12 KB, 24 KB with TTA) is read exactly
-// once with 128-bit streaming loads into registers; everything else lives in shared
-// memory; the only global write is the 28-byte record.
+// HBM-bound by design: every map (12 KB, 24 KB with TTA) is read exactly once; the only global
+// write is the 28-byte record.  One persistent CTA per SM, 16 warps, ONE WARP PER MAP:
+//   * one lane issues a 12 KB bulk async copy (TMA, cp.async.bulk, completion on the warp's own
+//     mbarrier) of the map into the warp's private shared-memory tile; 16 x 12 KB per SM are in
+//     flight, and the next map and the flipped pass are prefetched into L2 meanwhile,
+//   * max -> candidate set {z > max - T} compacted with ballots into a short list (a trained head
+//     leaves 2-3 pixels) -> Michelot's fixed point on the list = the exact
+//     sort / cumsum threshold of sparsemax,
+//   * the convolution is evaluated sparsely: every support pixel adds w * g(dy) g(dx) (incl. its
+//     reflections) into the warp's private 64 x 48 shared-memory tile; the arg max is searched only
+//     over the rows of the support's bounding box (the OKS kernel is non-negative and decreasing,
+//     so the maximum of C cannot lie outside it),
+//   * all reductions are warp shuffles: no block barrier on this path.
+// Maps that are not sparse (flat random-init logits, arbitrary / negative heatmaps handed to the
+// public codec API) are queued and handled by the whole CTA with a dense separable convolution
+// (decode_dense) between batches of sparse maps - correct for any input, just not HBM-bound.
 #include "common.cuh"
 
 #include <math.h>
@@ -21,7 +33,14 @@ namespace pp {
 
 constexpr int kMaxRadius = 9;  // ceil(3 * 3.0): the variance is clipped to <= 3.0
 constexpr int kTaps = 2 * kMaxRadius + 1;
-constexpr int kDecodeThreads = 256;
+constexpr int kDecWarps = 16;
+constexpr int kDecThreads = 32 * kDecWarps;
+constexpr int kDenseWarps = 8;   // warps that run the dense path (3 float4 of the map per thread)
+constexpr int kDenseThreads = 32 * kDenseWarps;
+constexpr int kListCap = 128;   // candidates per map kept in the compact list
+constexpr int kSrcCap = 2 * kListCap;
+constexpr int kQueueThresh = 16;  // deferred (dense) maps that trigger a cooperative pass
+constexpr int kQueueCap = kQueueThresh + 2 * kDecWarps;  // every warp may still deliver its current and its prefetched map
 
 struct DecodeParams {
   const float* maps;
@@ -31,17 +50,50 @@ struct DecodeParams {
   float* records;
   float* merged_out;
   int num_kpts;
+  int count;  // batch * num_kpts maps
   int is_logits;
-  float temperature, normalize, err_div;
+  int temp_is_pow2;
+  float temperature, inv_temperature, normalize, err_div;
   int flip_idx[PP_MAX_KEYPOINTS];
   int radius[PP_MAX_KEYPOINTS];
   float taps[PP_MAX_KEYPOINTS][kTaps + 1];  // 1-D factor g of the OKS kernel, sum 1
 };
 
-// Block-wide all-reduce of N values through double-buffered scratch: one barrier per call
-// (a thread can be at most one reduction ahead of the slowest).
+__device__ __forceinline__ int reflect(int i, int n) {  // scipy 'reflect': d c b a | a b c d | d c b a
+  return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One quadratic sub-pixel step on the convolved map (post_processing.py:384-430), fp32 like the reference.
+__device__ __forceinline__ void subpixel(float c, float l, float r, float up, float dn, float& lx, float& ly) {
+  const float dx = __fmul_rn(__fsub_rn(r, l), 0.5f), dy = __fmul_rn(__fsub_rn(dn, up), 0.5f);
+  float dxx = __fsub_rn(__fadd_rn(r, l), __fmul_rn(2.f, c));
+  float dyy = __fsub_rn(__fadd_rn(dn, up), __fmul_rn(2.f, c));
+  if (dxx == 0.f) dxx = 1e-6f;
+  if (dyy == 0.f) dyy = 1e-6f;
+  lx = __fadd_rn(lx, __fdiv_rn(-dx, dxx));
+  ly = __fadd_rn(ly, __fdiv_rn(-dy, dyy));
+}
+
+__device__ __forceinline__ void write_scalars(const DecodeParams& p, int b, int k, int kf, int j) {
+  float s = 0.f;
+  const int K = p.num_kpts;
+  if (p.scal) {
+    s = p.scal[(size_t)(b * 4 + j) * K + k];
+    if (p.scal_flip) s = (s + p.scal_flip[(size_t)(b * 4 + j) * K + kf]) * 0.5f;
+    if (j == 3) s = s / p.err_div;
+  }
+  p.records[(size_t)(b * K + k) * PP_RECORD_FLOATS + 3 + j] = s;
+}
+
+// =================================================================================================
+// Dense path: the whole CTA on one map (any input).  Shared memory: three H x W planes + scratch.
+// =================================================================================================
+__device__ __forceinline__ void dense_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kDenseThreads) : "memory"); }
+
 template <int N, typename T, typename Op>
-__device__ __forceinline__ void block_allreduce(T (&v)[N], T (*scratch)[kDecodeThreads / 32][4], int& parity, Op op) {
+__device__ __forceinline__ void block_allreduce(T (&v)[N], T (*scratch)[kDenseWarps][4], int& parity, Op op) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -52,56 +104,45 @@ __device__ __forceinline__ void block_allreduce(T (&v)[N], T (*scratch)[kDecodeT
 #pragma unroll
     for (int i = 0; i < N; ++i) scratch[parity][warp][i] = v[i];
   }
-  __syncthreads();
+  dense_sync();
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     T r = scratch[parity][0][i];
 #pragma unroll
-    for (int w = 1; w < kDecodeThreads / 32; ++w) r = op(r, scratch[parity][w][i]);
+    for (int w = 1; w < kDenseWarps; ++w) r = op(r, scratch[parity][w][i]);
     v[i] = r;
   }
   parity ^= 1;
 }
 
-__device__ __forceinline__ int reflect(int i, int n) {  // scipy 'reflect': d c b a | a b c d | d c b a
-  return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i);
-}
-
 template <int H, int W>
-__global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeParams p) {
+__device__ __noinline__ void decode_dense(const DecodeParams& p, int item, float* sP, float* sH, float* sC,
+                             float (*red_f)[kDenseWarps][4], int (*red_i)[kDenseWarps][4]) {
   constexpr int NPX = H * W;
   constexpr int NV4 = NPX / 4;
-  constexpr int T = kDecodeThreads;
+  constexpr int T = kDenseThreads;
   constexpr int V = NV4 / T;
   static_assert(NV4 % T == 0 && W % 4 == 0, "map must split into whole float4 per thread");
-
-  __shared__ __align__(16) float sP[NPX];  // merged, normalised heatmap
-  __shared__ __align__(16) float sH[NPX];  // after the horizontal pass
-  __shared__ __align__(16) float sC[NPX];  // convolved map
-  __shared__ float red_f[2][T / 32][4];
-  __shared__ int red_i[2][T / 32][4];
   int par_f = 0, par_i = 0;
-
   const int tid = threadIdx.x;
   const int K = p.num_kpts;
-  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  const int b = item / K, k = item % K;
   const bool tta = p.maps_flip != nullptr;
   const int kf = tta ? p.flip_idx[k] : k;
 
-  // ---- 1. stream the map(s) into registers ------------------------------------------------
   float z1[V][4], z2[V][4];
   {
     const float4* s1 = reinterpret_cast<const float4*>(p.maps + (size_t)(b * K + k) * NPX);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float4 t = ld_stream_f4(s1 + tid + j * T);
+      const float4 t = ld_stream_f4(s1 + tid + j * T);
       z1[j][0] = t.x; z1[j][1] = t.y; z1[j][2] = t.z; z1[j][3] = t.w;
     }
     if (tta) {
       const float4* s2 = reinterpret_cast<const float4*>(p.maps_flip + (size_t)(b * K + kf) * NPX);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float4 t = ld_stream_f4(s2 + tid + j * T);
+        const float4 t = ld_stream_f4(s2 + tid + j * T);
         z2[j][0] = t.x; z2[j][1] = t.y; z2[j][2] = t.z; z2[j][3] = t.w;
       }
     } else {
@@ -110,7 +151,6 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
     }
   }
 
-  // ---- 2. sparsemax(z / T) * normalize, clamp to [0, 1] (both passes together) -----------
   if (p.is_logits) {
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -127,7 +167,6 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
     for (int j = 0; j < V; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { z1[j][c] -= mx[0]; z2[j][c] -= mx[1]; }
-
     // Michelot's fixed point on the candidate set {z > -1} (a superset of the support):
     // tau <- (sum_{z > tau} z - 1) / #{z > tau} until the set stops shrinking.
     float thr[2] = {-1.f, -1.f}, tau[2] = {-1.f, -1.f};
@@ -163,12 +202,12 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
       }
   }
 
-  // ---- 3. flip-TTA merge into shared memory ----------------------------------------------
+  // flip-TTA merge into shared memory
 #pragma unroll
   for (int j = 0; j < V; ++j)
     reinterpret_cast<float4*>(sP)[tid + j * T] = make_float4(z1[j][0], z1[j][1], z1[j][2], z1[j][3]);
   if (tta) {
-    __syncthreads();
+    dense_sync();
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int v4 = tid + j * T;          // float4 index in the flipped map
@@ -182,10 +221,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
       reinterpret_cast<float4*>(sP)[dst] = a;
     }
   }
-  __syncthreads();
+  dense_sync();
 
-  // ---- 4. support bounding box (any negative value -> treat the map as dense) -------------
-  int box[4] = {H, -1, W, -1};  // ymin, ymax, xmin, xmax ; reduce (min, max, min, max) as max of negated
+  // support bounding box (any negative value -> treat the map as dense)
+  int box[4] = {H, -1, W, -1};
   int neg = 0;
   float4* gout = p.merged_out ? reinterpret_cast<float4*>(p.merged_out + (size_t)(b * K + k) * NPX) : nullptr;
 #pragma unroll
@@ -213,7 +252,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
     if (ng[0]) { box[0] = 0; box[1] = H - 1; box[2] = 0; box[3] = W - 1; }
   }
 
-  // ---- 5. separable OKS convolution over the dilated box, argmax --------------------------
+  // separable OKS convolution over the dilated box, argmax
   const int rad = p.radius[k];
   const float* g = p.taps[k];
   float best = -INFINITY;
@@ -232,7 +271,7 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
       for (int d = -rad; d <= rad; ++d) acc = fmaf(g[d + rad], row[reflect(x + d, W)], acc);
       sH[y * W + x] = acc;
     }
-    __syncthreads();
+    dense_sync();
     const int nv = (Y1 - Y0 + 1) * wx;
     for (int i = tid; i < nv; i += T) {
       const int y = Y0 + i / wx, x = X0 + i % wx;
@@ -245,7 +284,6 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
       if (acc > best) { best = acc; best_i = y * W + x; }  // i ascending => first max per thread
     }
   }
-  // block arg-max, smallest flat index wins ties (np.argmax semantics)
   {
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -255,12 +293,10 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
       if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
     }
     if (lane == 0) { red_f[par_f][warp][0] = best; red_i[par_i][warp][0] = best_i; }
-    __syncthreads();  // also orders the sC writes before thread 0 reads them
+    dense_sync();  // also orders the sC writes before thread 0 reads them
   }
-
-  // ---- 6. sub-pixel step + record ----------------------------------------------------------
   if (tid == 0) {
-    for (int w = 0; w < T / 32; ++w) {
+    for (int w = 0; w < kDenseWarps; ++w) {
       const float ov = red_f[par_f][w][0];
       const int oi = red_i[par_i][w][0];
       if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
@@ -274,31 +310,473 @@ __global__ void __launch_bounds__(kDecodeThreads, 4) decode_kernel(const DecodeP
       return (nonempty && y >= Y0 && y <= Y1 && x >= X0 && x <= X1) ? sC[y * W + x] : 0.f;
     };
     float lx = (float)xs, ly = (float)ys;
-    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {
-      const float c = cval(ys, xs), r = cval(ys, xs + 1), l = cval(ys, xs - 1);
-      const float dn = cval(ys + 1, xs), up = cval(ys - 1, xs);
-      const float dx = __fmul_rn(__fsub_rn(r, l), 0.5f), dy = __fmul_rn(__fsub_rn(dn, up), 0.5f);
-      float dxx = __fsub_rn(__fadd_rn(r, l), __fmul_rn(2.f, c));
-      float dyy = __fsub_rn(__fadd_rn(dn, up), __fmul_rn(2.f, c));
-      if (dxx == 0.f) dxx = 1e-6f;
-      if (dyy == 0.f) dyy = 1e-6f;
-      lx = __fadd_rn(lx, __fdiv_rn(-dx, dxx));
-      ly = __fadd_rn(ly, __fdiv_rn(-dy, dyy));
-    }
+    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1)
+      subpixel(cval(ys, xs), cval(ys, xs - 1), cval(ys, xs + 1), cval(ys - 1, xs), cval(ys + 1, xs), lx, ly);
     float* rec = p.records + (size_t)(b * K + k) * PP_RECORD_FLOATS;
     rec[0] = lx;
     rec[1] = ly;
     rec[2] = sP[best_i];
   }
-  if (tid >= 32 && tid < 36) {  // the four scalar branches: prob, vis, oks, err
-    const int j = tid - 32;
-    float s = 0.f;
-    if (p.scal) {
-      s = p.scal[(size_t)(b * 4 + j) * K + k];
-      if (p.scal_flip) s = (s + p.scal_flip[(size_t)(b * 4 + j) * K + kf]) * 0.5f;
-      if (j == 3) s = s / p.err_div;
+  if (tid >= 32 && tid < 36) write_scalars(p, b, k, kf, tid - 32);
+  dense_sync();  // the planes are reused by the next deferred map
+}
+
+// =================================================================================================
+// Sparse path: one warp per map.
+// =================================================================================================
+struct __align__(16) WarpScratch {
+  float tile[64 * 48];          // the raw map while it is sparsified, then the convolved map C
+                                // (only the rows around the support are valid)
+  float val[kSrcCap];           // candidate / source values
+  unsigned short idx[kSrcCap];  // flat pixel index of each candidate / source
+  float fac[kTaps + 1];         // weight * row factors of the source being accumulated
+  unsigned long long bar;       // mbarrier of the bulk copies into `tile`
+};
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), m = (uint32_t)__cvta_generic_to_shared(bar);
+  // earlier generic-proxy accesses of the tile are ordered before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t m = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    if (++spins > (1u << 24)) __trap();  // a lost copy must surface as an error, never hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok) : "r"(m), "r"(parity) : "memory");
+  }
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+// Waits for the map in the warp's tile and compacts its candidates - logits: {z > max - T}, a superset
+// of the sparsemax support; heatmaps: the positive pixels - into the list (idx, raw val) at
+// list[off...].  Returns the number of entries, or -1 when the map is not sparse enough for this
+// path (too many candidates, or negative heatmap values).  `mx` returns the maximum (logits).
+// After the trailing __syncwarp the tile is free again.
+template <int H, int W>
+__device__ __forceinline__ int warp_compact(const DecodeParams& p, WarpScratch& ws, int off, int lane, uint32_t& phase,
+                                            float& mx) {
+  constexpr int NV = H * W / 128;  // float4 per lane
+  bulk_wait(&ws.bar, phase);
+  phase ^= 1u;
+  const float4* t4 = reinterpret_cast<const float4*>(ws.tile);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // one pass over the tile: per-float4 maxima stay in registers, so the candidate mask needs no re-read
+  float m4[NV];
+  float lo = 0.f;
+  mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 q = t4[lane + 32 * j];
+    m4[j] = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
+    mx = fmaxf(mx, m4[j]);
+    if (!p.is_logits) lo = fminf(lo, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
+  }
+  float thr = 0.f;
+  if (p.is_logits) {
+    mx = warp_max(mx);
+    // candidates: z / T > max / T - 1.  The raw-domain test is made slightly generous (any superset
+    // of the support gives the same threshold); the exact scaled values are formed per candidate.
+    thr = mx - p.temperature * 1.000001f - 1e-30f;
+  } else if (__any_sync(0xffffffffu, lo < 0.f)) {
+    // negative values break the "maximum lies inside the support's bounding box" argument
+    __syncwarp();
+    return -1;
+  }
+  unsigned jm = 0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) jm |= (m4[j] > thr ? 1u : 0u) << j;
+  jm = __reduce_or_sync(0xffffffffu, jm);
+  // ballot compaction of {e > thr} for the few float4 columns that hold a candidate
+  int n = 0;
+  while (jm) {
+    const int j = __ffs(jm) - 1;
+    jm &= jm - 1;
+    const float4 q = t4[lane + 32 * j];
+    const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool take = e[c] > thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, take);
+      const int add = __popc(bal);
+      if (n + add <= kListCap) {  // warp-uniform; on overflow only the count keeps growing
+        if (take) {
+          const int pos = off + n + __popc(bal & lt_mask);
+          ws.val[pos] = e[c];
+          ws.idx[pos] = (unsigned short)((lane + 32 * j) * 4 + c);
+        }
+      }
+      n += add;
     }
-    p.records[(size_t)(b * K + k) * PP_RECORD_FLOATS + 3 + j] = s;
+    if (n > kListCap) break;  // does not fit: not sparse
+  }
+  __syncwarp();
+  return n > kListCap ? -1 : n;
+}
+
+// List entries (pixel index, raw value) -> (y << 8 | x, heatmap value): sparsemax threshold by
+// Michelot's fixed point on the list (logits), mirror of the flipped pass.
+template <int H, int W>
+__device__ __forceinline__ void warp_finish_list(const DecodeParams& p, WarpScratch& ws, int off, int n, int mirror, float mx,
+                                                 int lane) {
+  for (int i = lane; i < n; i += 32) {
+    const int px = ws.idx[off + i];
+    const int y = px / W, x = px % W;
+    ws.idx[off + i] = (unsigned short)((y << 8) | (mirror ? W - 1 - x : x));
+  }
+  if (p.is_logits) {
+    // tau <- (sum_{z > tau} z - 1) / #{z > tau} until the set stops shrinking = the sort / cumsum
+    // threshold of Martins & Astudillo, Alg. 1 (on z - max z).
+    const float mxs = p.temp_is_pow2 ? mx * p.inv_temperature : mx / p.temperature;
+    auto scaled = [&](float e) { return (p.temp_is_pow2 ? e * p.inv_temperature : e / p.temperature) - mxs; };
+    float tau = -1.f;
+    if (n <= 32) {  // the usual case: one candidate per lane
+      const float z = lane < n ? scaled(ws.val[off + lane]) : -INFINITY;
+      float thr2 = -1.f;
+      int prev = -1;
+      for (int it = 0; it < 34; ++it) {
+        const bool in = z > thr2;
+        const float sum = warp_sum(in ? z : 0.f);
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        tau = (sum - 1.f) / (float)cnt;  // cnt >= 1: the maximum (z == 0) is always a candidate
+        if (cnt == prev) break;
+        prev = cnt;
+        thr2 = fmaxf(thr2, tau);
+      }
+      if (lane < n) ws.val[off + lane] = fminf(fmaxf(fmaxf(z - tau, 0.f) * p.normalize, 0.f), 1.f);
+    } else {
+      float zc[kListCap / 32];
+#pragma unroll
+      for (int i = 0; i < kListCap / 32; ++i) zc[i] = (lane + 32 * i < n) ? scaled(ws.val[off + lane + 32 * i]) : -INFINITY;
+      float thr2 = -1.f;
+      int prev = -1;
+      for (int it = 0; it < kListCap + 2; ++it) {
+        float sum = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < kListCap / 32; ++i)
+          if (zc[i] > thr2) { sum += zc[i]; ++cnt; }
+        sum = warp_sum(sum);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        tau = (sum - 1.f) / (float)cnt;
+        if (cnt == prev) break;
+        prev = cnt;
+        thr2 = fmaxf(thr2, tau);
+      }
+#pragma unroll
+      for (int i = 0; i < kListCap / 32; ++i)
+        if (lane + 32 * i < n) ws.val[off + lane + 32 * i] = fminf(fmaxf(fmaxf(zc[i] - tau, 0.f) * p.normalize, 0.f), 1.f);
+    }
+  }
+  __syncwarp();
+}
+
+// The sparse decode of one map whose first pass sits (or is arriving) in the warp's tile.
+// `issue_next` starts the bulk copy of the warp's next map as soon as the tile is free for it.
+// Returns false when the map has to go through the dense path.
+template <int H, int W, typename IssueNext>
+__device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, WarpScratch& ws, const float (*s_taps)[kTaps + 1],
+                                              int lane, uint32_t& phase, IssueNext&& issue_next) {
+  constexpr int NPX = H * W;
+  const int K = p.num_kpts;
+  const int b = item / K, k = item % K;
+  const bool tta = p.maps_flip != nullptr;
+  const int kf = tta ? p.flip_idx[k] : k;
+
+  float mx1, mx2 = 0.f;
+  const int n1 = warp_compact<H, W>(p, ws, 0, lane, phase, mx1);
+  if (n1 < 0) { issue_next(); return false; }
+  int n = n1;
+  if (tta) {
+    if (lane == 0) bulk_load(ws.tile, p.maps_flip + (size_t)(b * K + kf) * NPX, NPX * 4, &ws.bar);
+    warp_finish_list<H, W>(p, ws, 0, n1, 0, mx1, lane);  // overlaps the flipped pass's copy
+    const int n2 = warp_compact<H, W>(p, ws, n1, lane, phase, mx2);
+    if (n2 < 0) { issue_next(); return false; }
+    warp_finish_list<H, W>(p, ws, n1, n2, 1, mx2, lane);
+    // merged = (P + mirror(Pf)) * 0.5, pixel by pixel in fp32 exactly like the reference: an entry of
+    // the first list absorbs the matching entry of the second; unmatched entries are halved on their own
+    for (int i = lane; i < n1; i += 32) {
+      const unsigned short yx = ws.idx[i];
+      float other = 0.f;
+      for (int j = n1; j < n1 + n2; ++j) other = ws.idx[j] == yx ? ws.val[j] : other;
+      ws.val[i] = (ws.val[i] + other) * 0.5f;
+    }
+    __syncwarp();  // list-2 values are read above and rewritten below
+    for (int i = n1 + lane; i < n1 + n2; i += 32) {
+      const unsigned short yx = ws.idx[i];
+      bool dup = false;
+      for (int j = 0; j < n1; ++j) dup |= ws.idx[j] == yx;
+      ws.val[i] = dup ? 0.f : (0.f + ws.val[i]) * 0.5f;
+    }
+    n = n1 + n2;
+    __syncwarp();
+  } else {
+    warp_finish_list<H, W>(p, ws, 0, n1, 0, mx1, lane);
+  }
+
+  // ---- bounding box and size of the support ----
+  int ymin = H, ymax = -1, xmin = W, xmax = -1, nnz = 0;
+  for (int i = lane; i < n; i += 32) {
+    if (ws.val[i] != 0.f) {
+      const int yx = ws.idx[i], y = yx >> 8, x = yx & 255;
+      ymin = min(ymin, y); ymax = max(ymax, y); xmin = min(xmin, x); xmax = max(xmax, x);
+      ++nnz;
+    }
+  }
+  ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+  xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+  nnz = __reduce_add_sync(0xffffffffu, nnz);
+  const bool nonempty = ymax >= 0;
+
+  float4* gout = p.merged_out ? reinterpret_cast<float4*>(p.merged_out + (size_t)item * NPX) : nullptr;
+  if (gout) {
+#pragma unroll 4
+    for (int j = 0; j < NPX / 128; ++j) gout[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    for (int i = lane; i < n; i += 32)
+      if (ws.val[i] != 0.f) p.merged_out[(size_t)item * NPX + (ws.idx[i] >> 8) * W + (ws.idx[i] & 255)] = ws.val[i];
+  }
+
+  const int rad = p.radius[k];
+  const float* g = s_taps[k];  // shared-memory copy: the lookups below are lane-divergent
+  int best_i = 0;
+  float conf = 0.f, lx = 0.f, ly = 0.f;
+  bool issued = false;
+  if (nonempty) {
+    // The arg max of C lies inside the support's bounding box (the OKS kernel is non-negative and
+    // decreasing in |d|), extended to the border where a reflected image can pull it outwards.
+    const int sy0 = ymin <= rad - 1 ? 0 : ymin, sy1 = ymax >= H - rad ? H - 1 : ymax;
+    const int sx0 = xmin <= rad - 1 ? 0 : xmin, sx1 = xmax >= W - rad ? W - 1 : xmax;
+    const int bw = sx1 - sx0 + 1, area = (sy1 - sy0 + 1) * bw;
+    float best = -INFINITY;
+    best_i = 0x7fffffff;
+    float cc, cl, cr, cu, cd;  // C at the peak and its 4 neighbours
+    if (area <= 192) {  // direct evaluation costs ~area * nnz; the tile path ~200 * nnz + a scan of the rows
+      // ---- compact support: evaluate C = sum_s w_s g(dy) g(dx) (+ reflections) directly at the
+      // pixels of the box; the tile is not needed, so the next map's copy starts now ----
+      issue_next();
+      issued = true;
+      auto eval_c = [&](int qy, int qx) -> float {
+        float acc = 0.f;
+        for (int s = 0; s < n; ++s) {
+          const float w = ws.val[s];
+          if (w == 0.f) continue;  // warp-uniform
+          const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
+          const int dy = abs(qy - sy), dx = abs(qx - sx);
+          float fy = dy <= rad ? g[rad + dy] : 0.f;
+          float fx = dx <= rad ? g[rad + dx] : 0.f;
+          if (sy < rad || sy >= H - rad) {  // images at -1 - sy and 2H - 1 - sy (warp-uniform test)
+            const int d1 = qy + 1 + sy, d2 = 2 * H - 1 - sy - qy;
+            if (d1 <= rad) fy += g[rad + d1];
+            if (d2 <= rad) fy += g[rad + d2];
+          }
+          if (sx < rad || sx >= W - rad) {
+            const int d1 = qx + 1 + sx, d2 = 2 * W - 1 - sx - qx;
+            if (d1 <= rad) fx += g[rad + d1];
+            if (d2 <= rad) fx += g[rad + d2];
+          }
+          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(w, fy), fx));
+        }
+        return acc;
+      };
+      for (int q0 = 0; q0 < area; q0 += 32) {
+        const int q = min(q0 + lane, area - 1);  // the duplicate of the last pixel never wins a tie
+        const int qy = sy0 + q / bw, qx = sx0 + q % bw;
+        const float c = eval_c(qy, qx);
+        if (c > best) { best = c; best_i = qy * W + qx; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      }
+      if (!(best > 0.f)) best_i = 0;  // weights underflowed: C == 0 everywhere, first maximum is pixel 0
+      const int ys = best_i / W, xs = best_i % W;
+      // lanes 0..4: centre, left, right, up, down (clamped to the map; only used for interior peaks)
+      const int ddx = lane == 1 ? -1 : (lane == 2 ? 1 : 0), ddy = lane == 3 ? -1 : (lane == 4 ? 1 : 0);
+      const float v = eval_c(min(max(ys + ddy, 0), H - 1), min(max(xs + ddx, 0), W - 1));
+      cc = __shfl_sync(0xffffffffu, v, 0); cl = __shfl_sync(0xffffffffu, v, 1); cr = __shfl_sync(0xffffffffu, v, 2);
+      cu = __shfl_sync(0xffffffffu, v, 3); cd = __shfl_sync(0xffffffffu, v, 4);
+    } else {
+      // ---- scattered support: every source adds w * g(dy) g(dx) (+ reflections) into the warp's tile ----
+      const int zy0 = max(0, ymin - rad - 1), zy1 = min(H - 1, ymax + rad + 1);
+      float4* t4 = reinterpret_cast<float4*>(ws.tile);
+      for (int i = zy0 * (W / 4) + lane; i < (zy1 + 1) * (W / 4); i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      for (int s = 0; s < n; ++s) {
+        const float w = ws.val[s];
+        if (w == 0.f) continue;  // warp-uniform
+        const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
+        const int y0 = max(0, sy - rad), y1 = min(H - 1, sy + rad), x0 = max(0, sx - rad), x1 = min(W - 1, sx + rad);
+        // 1-D factors over the window: the direct tap plus the taps of the two reflected images;
+        // rows carry the weight, lanes keep their column factor in a register
+        float fx = 0.f;
+        if (lane <= 2 * rad) {
+          const int yy = y0 + lane, xx = x0 + lane;
+          if (yy <= y1) {
+            float f = g[rad + abs(yy - sy)];
+            const int d1 = yy + 1 + sy, d2 = 2 * H - 1 - sy - yy;
+            if (d1 <= rad) f += g[rad + d1];
+            if (d2 <= rad) f += g[rad + d2];
+            ws.fac[lane] = __fmul_rn(w, f);
+          }
+          if (xx <= x1) {
+            fx = g[rad + abs(xx - sx)];
+            const int d1 = xx + 1 + sx, d2 = 2 * W - 1 - sx - xx;
+            if (d1 <= rad) fx += g[rad + d1];
+            if (d2 <= rad) fx += g[rad + d2];
+          }
+        }
+        __syncwarp();
+        if (x0 + lane <= x1) {  // lane = window column; the window rows are independent read-modify-writes
+          float* c = ws.tile + y0 * W + x0 + lane;
+          const int rows = y1 - y0 + 1;
+          float cv[kTaps];
+#pragma unroll
+          for (int dy = 0; dy < kTaps; ++dy)
+            if (dy < rows) cv[dy] = c[dy * W];
+#pragma unroll
+          for (int dy = 0; dy < kTaps; ++dy)
+            if (dy < rows) c[dy * W] = __fadd_rn(cv[dy], __fmul_rn(ws.fac[dy], fx));
+        }
+        __syncwarp();
+      }
+      // first arg max over the rows of the search box
+      for (int i = sy0 * (W / 4) + lane; i < (sy1 + 1) * (W / 4); i += 32) {
+        const float4 c = t4[i];
+        if (c.x > best) { best = c.x; best_i = 4 * i; }
+        if (c.y > best) { best = c.y; best_i = 4 * i + 1; }
+        if (c.z > best) { best = c.z; best_i = 4 * i + 2; }
+        if (c.w > best) { best = c.w; best_i = 4 * i + 3; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      }
+      if (!(best > 0.f)) best_i = 0;
+      const float* c = ws.tile + best_i;
+      const int ys = best_i / W;
+      const bool in = ys >= 1 && ys < H - 1 && ys - 1 >= zy0 && ys + 1 <= zy1 && best_i % W >= 1 && best_i % W < W - 1;
+      cc = in ? c[0] : 0.f; cl = in ? c[-1] : 0.f; cr = in ? c[1] : 0.f; cu = in ? c[-W] : 0.f; cd = in ? c[W] : 0.f;
+      __syncwarp();  // the tile is read above and refilled by the next copy
+    }
+    const int ys = best_i / W, xs = best_i % W;
+    lx = (float)xs; ly = (float)ys;
+    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) subpixel(cc, cl, cr, cu, cd, lx, ly);
+    // conf = merged heatmap at the integer peak (at most one non-zero entry per pixel after the merge)
+    const int pyx = (ys << 8) | xs;
+    float cv = 0.f;
+    for (int i = lane; i < n; i += 32)
+      if (ws.idx[i] == pyx && ws.val[i] != 0.f) cv = ws.val[i];
+    conf = warp_sum(cv);
+  }
+  if (!issued) issue_next();
+  if (lane == 0) {
+    float* rec = p.records + (size_t)item * PP_RECORD_FLOATS;
+    rec[0] = lx;
+    rec[1] = ly;
+    rec[2] = conf;
+  }
+  if (lane >= 4 && lane < 8) write_scalars(p, b, k, kf, lane - 4);
+  __syncwarp();
+  return true;
+}
+
+struct __align__(16) DecodeSmem {
+  WarpScratch warp[kDecWarps];
+  float red_f[2][kDenseWarps][4];
+  int red_i[2][kDenseWarps][4];
+  float taps[PP_MAX_KEYPOINTS][kTaps + 1];
+  int queue[kQueueCap];
+  int q_count;
+  int next;   // next map of this CTA's range
+  int all_done;
+};
+
+template <int H, int W>
+__global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const __grid_constant__ DecodeParams p) {
+  constexpr int NPX = H * W;
+  static_assert(sizeof(WarpScratch) * kDecWarps >= 3 * NPX * sizeof(float), "dense planes alias the warp scratch");
+  extern __shared__ __align__(16) uint8_t dec_smem_raw[];
+  DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(dec_smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // this CTA's contiguous range of maps (balanced to +-1)
+  const int per = p.count / gridDim.x, rem = p.count % gridDim.x;
+  const int first = blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int cnt = per + ((int)blockIdx.x < rem ? 1 : 0);
+  if (threadIdx.x == 0) { sm.q_count = 0; sm.next = 0; sm.all_done = 0; }
+  for (int i = threadIdx.x; i < PP_MAX_KEYPOINTS * (kTaps + 1); i += kDecThreads) (&sm.taps[0][0])[i] = (&p.taps[0][0])[i];
+  if (lane == 0) {
+    const uint32_t m = (uint32_t)__cvta_generic_to_shared(&sm.warp[warp].bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool tta = p.maps_flip != nullptr;
+  uint32_t phase = 0;
+
+  // next map of this CTA's range for this warp, or -1 (range exhausted / dense queue filling up);
+  // its flipped pass and a map one round ahead are pulled towards L2 meanwhile
+  auto fetch = [&]() -> int {
+    int it = -1;
+    if (lane == 0) {
+      if (*reinterpret_cast<volatile int*>(&sm.q_count) < kQueueThresh) {
+        it = atomicAdd(&sm.next, 1);
+        if (it >= cnt) it = -1;
+      }
+      if (it >= 0) {
+        const int K = p.num_kpts, item = first + it;
+        if (tta) bulk_prefetch_l2(p.maps_flip + (size_t)((item / K) * K + p.flip_idx[item % K]) * NPX, NPX * 4);
+        if (it + kDecWarps < cnt) bulk_prefetch_l2(p.maps + (size_t)(item + kDecWarps) * NPX, NPX * 4);
+      }
+    }
+    return __shfl_sync(0xffffffffu, it, 0);
+  };
+  WarpScratch& ws = sm.warp[warp];
+
+  while (true) {
+    // ---- sparse phase: warps pull maps until the range is exhausted or the dense queue fills ----
+    int cur = fetch();
+    if (cur >= 0 && lane == 0) bulk_load(ws.tile, p.maps + (size_t)(first + cur) * NPX, NPX * 4, &ws.bar);
+    while (cur >= 0) {
+      int nxt = -2;  // not fetched yet
+      auto issue_next = [&]() {
+        __syncwarp();
+        nxt = fetch();
+        if (nxt >= 0 && lane == 0) bulk_load(ws.tile, p.maps + (size_t)(first + nxt) * NPX, NPX * 4, &ws.bar);
+      };
+      if (!decode_sparse<H, W>(p, first + cur, ws, sm.taps, lane, phase, issue_next)) {
+        if (lane == 0) sm.queue[atomicAdd(&sm.q_count, 1)] = first + cur;
+      }
+      cur = nxt;
+    }
+    __syncthreads();
+    // ---- dense phase: the whole CTA works through the queue ----
+    const int nq = sm.q_count;
+    float* planes = reinterpret_cast<float*>(&sm.warp[0]);
+    if (warp < kDenseWarps)
+      for (int q = 0; q < nq; ++q)
+        decode_dense<H, W>(p, sm.queue[q], planes, planes + NPX, planes + 2 * NPX, sm.red_f, sm.red_i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sm.q_count = 0;
+      sm.all_done = sm.next >= cnt ? 1 : 0;
+    }
+    __syncthreads();
+    if (sm.all_done) break;
   }
 }
 
@@ -348,6 +826,11 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
   p.num_kpts = cfg->num_keypoints;
   p.is_logits = cfg->input_is_logits;
   p.temperature = cfg->temperature; p.normalize = cfg->normalize;
+  p.inv_temperature = 1.0f / cfg->temperature;
+  {  // x / T == x * (1 / T) bit for bit when T is a power of two (the shipped 0.5)
+    int ex = 0;
+    p.temp_is_pow2 = cfg->input_is_logits && frexpf(cfg->temperature, &ex) == 0.5f;
+  }
   p.err_div = cfg->error_divisor > 0.f
                   ? cfg->error_divisor
                   : sqrtf((float)(cfg->height * cfg->height + cfg->width * cfg->width));
@@ -362,9 +845,23 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
   }
   fill_oks_taps(p, cfg->num_keypoints, cfg->height, cfg->width);
 
-  const int64_t grid = (int64_t)batch * cfg->num_keypoints;
-  PP_REQUIRE(grid < (1ll << 31), PP_ERR_INVALID, "pp_decode: batch too large");
-  decode_kernel<64, 48><<<(unsigned)grid, kDecodeThreads, 0, (cudaStream_t)stream>>>(p);
+  const int64_t count = (int64_t)batch * cfg->num_keypoints;
+  PP_REQUIRE(count < (1ll << 31), PP_ERR_INVALID, "pp_decode: batch too large");
+  p.count = (int)count;
+  static int sms = 0;
+  static bool attr_set = false;
+  auto kern = decode_kernel<64, 48>;
+  if (!attr_set) {
+    int dev = 0;
+    PP_CHECK_CUDA(cudaGetDevice(&dev));
+    PP_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+    attr_set = true;
+  }
+  // one persistent CTA per SM; with few maps, enough CTAs that every warp has one
+  const int64_t want = (count + kDecWarps - 1) / kDecWarps;
+  const int grid = (int)(want < sms ? want : sms);
+  kern<<<grid, kDecThreads, sizeof(DecodeSmem), (cudaStream_t)stream>>>(p);
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
