@@ -8,7 +8,8 @@
 //
 // One CTA per (image, head), 6 warps; a warp owns 16 query rows at a time and the WHOLE 192-key
 // score row lives in its registers, so softmax needs no online rescaling:
-//   S = Q K^T   mma.sync m16n8k16, K fragments by ldmatrix from padded shared memory
+//   S = Q K^T   mma.sync m16n8k16, K fragments by ldmatrix from padded shared memory, 96 keys at
+//               a time (the score chunk lives in registers; running max / sum between the chunks)
 //   P = exp2((S - rowmax) * scale * log2 e)                 fp32, row sums by quad shuffles
 //   O = P V     the S accumulator layout IS the A-fragment layout of the second product
 //   out = O / rowsum  -> written as the proj GEMM's A operand
@@ -77,7 +78,7 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
 
 // NTOK tokens, DH head width, SPLIT = 3 (FP16X3) or 1, BF16 element type for SPLIT == 1.
 template <int NTOK, int DH, int SPLIT, bool BF16>
-__global__ void __launch_bounds__(kAttThreads, DH == 32 ? 2 : 1)
+__global__ void __launch_bounds__(kAttThreads, DH == 32 ? 3 : 1)
 attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* __restrict__ out_op) {
   constexpr int NOPS = SPLIT == 3 ? 2 : 1;
   constexpr int KT = NTOK / 8;        // key tiles of 8
@@ -98,15 +99,16 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
 
   // ---- K, V (hi and lo planes) -> shared memory, 16-byte cp.async chunks ----
   {
-    constexpr int CPR = DH / 8;  // chunks per row per plane
-    constexpr int TOTAL = NTOK * CPR * 2 * NOPS;
-    for (int i = threadIdx.x; i < TOTAL; i += kAttThreads) {
-      const int c = i % CPR;
-      int t = i / CPR;
-      const int r = t % NTOK; t /= NTOK;
-      const int kv = t & 1, part = t >> 1;  // kv: 0 = K, 1 = V; part: 0 = hi, 1 = lo
-      const uint16_t* src = base + (size_t)r * RS + (1 + kv) * D + part * 3 * D + c * 8;
-      cp_async16(s_base + (kv * NOPS + part) * ARR + r * ROWB + c * 16, src);
+    constexpr int CPR = DH / 8;  // chunks per row per plane (a power of two)
+#pragma unroll
+    for (int pl = 0; pl < 2 * NOPS; ++pl) {
+      const int kv = pl / NOPS, part = pl % NOPS;  // kv: 0 = K, 1 = V; part: 0 = hi, 1 = lo
+      const uint16_t* src0 = base + (1 + kv) * D + part * 3 * D;
+      const uint32_t dst0 = s_base + pl * ARR;
+      for (int i = threadIdx.x; i < NTOK * CPR; i += kAttThreads) {
+        const int r = i / CPR, c = i % CPR;
+        cp_async16(dst0 + r * ROWB + c * 16, src0 + (size_t)r * RS + c * 8);
+      }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -140,90 +142,102 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
       }
     }
 
-    // ---- S = Q K^T: the full score rows of this warp's 16 queries, in registers ----
-    float s[KT][4];
-    // ldmatrix lane address: matrix (lane / 8) = 16-byte dh chunk, row = key (lane % 8)
-    const uint32_t k_lane = (uint32_t)((lane & 7) * ROWB + (lane >> 3) * 16);
-#pragma unroll
-    for (int nt = 0; nt < KT; ++nt) {
-      float a0[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int kp = 0; kp < KS / 2; ++kp) {  // one ldmatrix.x4 covers two k-steps (32 dh)
-        uint32_t kh[4], kl[4];
-        ldmatrix_x4(kh, sK[0] + nt * 8 * ROWB + kp * 64 + k_lane);
-        if constexpr (SPLIT == 3) ldmatrix_x4(kl, sK[1] + nt * 8 * ROWB + kp * 64 + k_lane);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int ks = kp * 2 + u;
-          mma16816<BF16>(a0, qh[ks], kh[2 * u], kh[2 * u + 1]);
-          if constexpr (SPLIT == 3) {
-            mma16816<BF16>(a0, qh[ks], kl[2 * u], kl[2 * u + 1]);
-            mma16816<BF16>(a0, ql[ks], kh[2 * u], kh[2 * u + 1]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s[nt][i] = a0[i];
-    }
-
-    // ---- softmax over the 192 keys (rows g and g + 8 of the tile) ----
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < KT; ++nt) {
-      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < KT; ++nt) {
-      s[nt][0] = exp2f(fmaf(s[nt][0] - mx0, c_exp, p_exp)); s[nt][1] = exp2f(fmaf(s[nt][1] - mx0, c_exp, p_exp));
-      s[nt][2] = exp2f(fmaf(s[nt][2] - mx1, c_exp, p_exp)); s[nt][3] = exp2f(fmaf(s[nt][3] - mx1, c_exp, p_exp));
-      l0 += s[nt][0] + s[nt][1];
-      l1 += s[nt][2] + s[nt][3];
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-    // ---- O = P V ----
+    // ---- keys in chunks of KC: S = Q K^T (registers) -> running max / sum -> O += P V ----
+    // (flash-style rescaling between the chunks; exact softmax up to fp32 rounding)
+    constexpr int KC = 48, KTC = KC / 8, NCH = NTOK / KC;
+    static_assert(NTOK % KC == 0 && KTC % 2 == 0, "key chunking");
     float o0[DT][4];
 #pragma unroll
     for (int dt = 0; dt < DT; ++dt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) o0[dt][i] = 0.f;
+    float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    // ldmatrix lane address: matrix (lane / 8) = 16-byte dh chunk, row = key (lane % 8)
+    const uint32_t k_lane = (uint32_t)((lane & 7) * ROWB + (lane >> 3) * 16);
     // ldmatrix.trans lane address: matrices {keys 0-7, keys 8-15} x {dh chunk c, c + 1}
     const uint32_t v_lane = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * ROWB + (lane >> 4) * 16);
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+      float s[KTC][4];
 #pragma unroll
-    for (int j = 0; j < KT / 2; ++j) {  // k-steps of 16 keys
-      uint32_t ph[4], pl[4];
-      if constexpr (SPLIT == 3) {
-        split2(s[2 * j][0], s[2 * j][1], ph[0], pl[0]);
-        split2(s[2 * j][2], s[2 * j][3], ph[1], pl[1]);
-        split2(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
-        split2(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
-      } else {
-        ph[0] = pack2<BF16>(s[2 * j][0], s[2 * j][1]);
-        ph[1] = pack2<BF16>(s[2 * j][2], s[2 * j][3]);
-        ph[2] = pack2<BF16>(s[2 * j + 1][0], s[2 * j + 1][1]);
-        ph[3] = pack2<BF16>(s[2 * j + 1][2], s[2 * j + 1][3]);
+      for (int nt = 0; nt < KTC; ++nt) {
+        float a0[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t krow = (uint32_t)((ch * KTC + nt) * 8 * ROWB);
+#pragma unroll
+        for (int kp = 0; kp < KS / 2; ++kp) {  // one ldmatrix.x4 covers two k-steps (32 dh)
+          uint32_t kh[4], kl[4];
+          ldmatrix_x4(kh, sK[0] + krow + kp * 64 + k_lane);
+          if constexpr (SPLIT == 3) ldmatrix_x4(kl, sK[1] + krow + kp * 64 + k_lane);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int ks = kp * 2 + u;
+            mma16816<BF16>(a0, qh[ks], kh[2 * u], kh[2 * u + 1]);
+            if constexpr (SPLIT == 3) {
+              mma16816<BF16>(a0, qh[ks], kl[2 * u], kl[2 * u + 1]);
+              mma16816<BF16>(a0, ql[ks], kh[2 * u], kh[2 * u + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[nt][i] = a0[i];
       }
+      // running max over the rows g and g + 8 of the tile
+      float c0 = mx0, c1 = mx1;
 #pragma unroll
-      for (int dp = 0; dp < DT / 2; ++dp) {  // one ldmatrix.x4.trans covers two 8-wide dh tiles
-        uint32_t vh[4], vl[4];
-        ldmatrix_x4_trans(vh, sV[0] + j * 16 * ROWB + dp * 32 + v_lane);
-        if constexpr (SPLIT == 3) ldmatrix_x4_trans(vl, sV[1] + j * 16 * ROWB + dp * 32 + v_lane);
+      for (int nt = 0; nt < KTC; ++nt) {
+        c0 = fmaxf(c0, fmaxf(s[nt][0], s[nt][1]));
+        c1 = fmaxf(c1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1)); c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+      c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+      const float r0 = exp2f((mx0 - c0) * c_exp), r1 = exp2f((mx1 - c1) * c_exp);  // exp2(-inf) = 0 on the first chunk
+      mx0 = c0; mx1 = c1;
+      l0 *= r0; l1 *= r1;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int dt = dp * 2 + u;
-          mma16816<BF16>(o0[dt], ph, vh[2 * u], vh[2 * u + 1]);
-          if constexpr (SPLIT == 3) {
-            mma16816<BF16>(o0[dt], ph, vl[2 * u], vl[2 * u + 1]);
-            mma16816<BF16>(o0[dt], pl, vh[2 * u], vh[2 * u + 1]);
+      for (int dt = 0; dt < DT; ++dt) { o0[dt][0] *= r0; o0[dt][1] *= r0; o0[dt][2] *= r1; o0[dt][3] *= r1; }
+#pragma unroll
+      for (int nt = 0; nt < KTC; ++nt) {
+        s[nt][0] = exp2f(fmaf(s[nt][0] - mx0, c_exp, p_exp)); s[nt][1] = exp2f(fmaf(s[nt][1] - mx0, c_exp, p_exp));
+        s[nt][2] = exp2f(fmaf(s[nt][2] - mx1, c_exp, p_exp)); s[nt][3] = exp2f(fmaf(s[nt][3] - mx1, c_exp, p_exp));
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+      // O += P V for this chunk's keys
+#pragma unroll
+      for (int j = 0; j < KTC / 2; ++j) {  // k-steps of 16 keys
+        uint32_t ph[4], pl[4];
+        if constexpr (SPLIT == 3) {
+          split2(s[2 * j][0], s[2 * j][1], ph[0], pl[0]);
+          split2(s[2 * j][2], s[2 * j][3], ph[1], pl[1]);
+          split2(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
+          split2(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
+        } else {
+          ph[0] = pack2<BF16>(s[2 * j][0], s[2 * j][1]);
+          ph[1] = pack2<BF16>(s[2 * j][2], s[2 * j][3]);
+          ph[2] = pack2<BF16>(s[2 * j + 1][0], s[2 * j + 1][1]);
+          ph[3] = pack2<BF16>(s[2 * j + 1][2], s[2 * j + 1][3]);
+        }
+        const uint32_t vrow = (uint32_t)((ch * KC + j * 16) * ROWB);
+#pragma unroll
+        for (int dp = 0; dp < DT / 2; ++dp) {  // one ldmatrix.x4.trans covers two 8-wide dh tiles
+          uint32_t vh[4], vl[4];
+          ldmatrix_x4_trans(vh, sV[0] + vrow + dp * 32 + v_lane);
+          if constexpr (SPLIT == 3) ldmatrix_x4_trans(vl, sV[1] + vrow + dp * 32 + v_lane);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int dt = dp * 2 + u;
+            mma16816<BF16>(o0[dt], ph, vh[2 * u], vh[2 * u + 1]);
+            if constexpr (SPLIT == 3) {
+              mma16816<BF16>(o0[dt], ph, vl[2 * u], vl[2 * u + 1]);
+              mma16816<BF16>(o0[dt], pl, vh[2 * u], vh[2 * u + 1]);
+            }
           }
         }
       }
     }
+    // the per-lane partial row sums (4 lanes share a row)
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 
     // ---- normalise and write the proj GEMM's A operand (rows b*NTOK + ..., cols h*DH + ...) ----
     // FP16X3: O carries 64 (P) * 64 (V) and the row sum carries 64, so O / l is already in operand units

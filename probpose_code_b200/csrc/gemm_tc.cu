@@ -645,7 +645,15 @@ int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaSt
              "pp_gemm: %d taps need k=%d to split into multiples of %d", tp.taps, a.k, kBK);
   tp.tap_k = a.k / tp.taps;
   for (int t = 0; t < tp.taps; ++t) tp.shift[t] = a.a_taps > 1 ? a.a_tap_shift[t] : 0;
-  const int bn = tile_n > 0 ? tile_n : pick_tile_n(a.n, a.k, a.precision);
+  int bn = tile_n > 0 ? tile_n : pick_tile_n(a.n, a.k, a.precision);
+  if (tile_n <= 0 && a.out_kind != PP_OUT_PLANES) {
+    // few rows (the pooled 4x4 / 2x2 stages of the scalar branches): narrower tiles spread the long
+    // K loop over more SMs - with fewer tiles than SMs the time is K / 16 x 3 x BN / 2 cycles per tile
+    const int64_t mt = (a.m + kBM - 1) / kBM;
+    const int widths[3] = {128, 64, 32};
+    for (int i = 0; i < 3 && mt * ((a.n + bn - 1) / bn) < num_sms(); ++i)
+      if (widths[i] < bn) bn = widths[i];
+  }
   const int accs = (a.precision == PP_PREC_FP16X3 && a.k > kTwoAccMinK && bn <= 128) ? 2 : 1;
   // CTA pairs pay off once there are enough 256-row tiles to occupy the 74 TPCs
   const bool pair = a.cta_pair == 2 || (a.cta_pair == 0 && (int64_t)((a.m + 255) / 256) * ((a.n + bn - 1) / bn) >= num_sms() / 2);
