@@ -53,22 +53,110 @@ def load_peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def load_traffic() -> dict:
+    """DRAM bytes per launch from the committed ncu capture (tools/ncu_traffic.py -> profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def decode_leg(eng, dev, fi, batch: int = 256, sets: int = 4, iters: int = 40) -> dict:
+    from probpose_code_b200 import ops, synth
+    mean = torch.tensor(eng_mean(), device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(eng_std(), device=dev).view(1, 3, 1, 1)
+    chunk = min(eng.max_batch, 64)
+    zs, zfs = [], []
+    for s_ in range(sets):
+        parts, parts_f = [], []
+        for c0 in range(0, batch, chunk):
+            crops = synth.make_crops(chunk, seed=5000 + 100 * s_ + c0).to(dev)
+            x = ((crops[:, [2, 1, 0]].float() - mean) / std).contiguous()
+            parts.append(eng.head(eng.backbone(x))[0])
+            parts_f.append(eng.head(eng.backbone(x.flip(-1).contiguous()))[0])
+        zs.append(torch.cat(parts).contiguous())
+        zfs.append(torch.cat(parts_f).contiguous())
+    rec = torch.empty((batch, 17, 7), dtype=torch.float32, device=dev)
+    out = {}
+    for name, tta in (("plain", False), ("tta", True)):
+        def run(i):
+            if tta:
+                ops.decode(zs[i % sets], zfs[i % sets], fi, input_is_logits=True, out=rec)
+            else:
+                ops.decode(zs[i % sets], input_is_logits=True, out=rec)
+        for i in range(sets):
+            run(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            run(i)
+        b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / iters
+        nbytes = DECODE_BYTES_PER_PERSON[tta] * batch
+        out[name] = dict(us=us, bytes=nbytes, gbs=nbytes / us / 1e3)
+    return out
+
+
+def eng_mean():
+    from probpose_code_b200.engine import PIXEL_MEAN
+    return list(PIXEL_MEAN)
+
+
+def eng_std():
+    from probpose_code_b200.engine import PIXEL_STD
+    return list(PIXEL_STD)
+
+
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md 'clocks' line)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md 'clocks' line):
+    NVML every 10 ms when nvidia_ml_py is importable, else nvidia-smi polling."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.index, self.mhz, self.max_mhz, self.reasons, self.stop_flag, self.thread = index, [], None, set(), False, None
+        self.how = "nvidia-smi"
+
+    def _run_nvml(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        except Exception:  # noqa: BLE001
+            return False
+        self.how = "nvml"
+        while not self.stop_flag:
+            try:
+                self.mhz.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.reasons.update(k for k, bit in names.items() if r & bit)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+        return True
 
     def _run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                f = [x.strip() for x in out.split(",")]
+                if f and f[0].isdigit():
+                    self.mhz.append(int(f[0]))
+                    self.max_mhz = int(f[1]) if f[1].isdigit() else self.max_mhz
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(0.1)
@@ -81,15 +169,9 @@ class ClockSampler:
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None,
-                    sm_max_mhz=int(self.samples[0][1]) if self.samples and self.samples[0][1].isdigit() else None,
-                    reasons=sorted(reasons), samples=len(self.samples))
+        sm = sorted(self.mhz)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(sm), how=self.how)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -145,6 +227,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="crops per GPU per step")
     ap.add_argument("--no-flip", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode-leg", action="store_true", help="skip the batch-256 decode-kernel leg (ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     flip = not args.no_flip
@@ -231,6 +314,10 @@ def main():
         eng.infer(resident[i % n_rot], flip_test=flip, flip_indices=fi, out=rec)
     prof = eng.profile_end()
 
+    # ---- the fused decode kernel alone at BASELINE config 3 (batch 256): logits of this model for 256
+    # crops, 4 rotating sets (> 126 MB L2 between reuses), back-to-back launches between one event pair
+    dec256 = decode_leg(eng, dev, fi) if (rank == 0 and not args.no_decode_leg) else None
+
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -238,6 +325,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
+        traffic = load_traffic()
         passes = 2 if flip else 1
         persons = world * B * args.steps
         gemm = prof["gemm"]
@@ -261,14 +349,23 @@ def main():
                      d2h_bytes_per_step=B * 17 * 7 * 4, api="TopdownPoseEstimator.test_step(pinned uint8 crops) -> host numpy"),
             gpu_launches=int(launches) * args.steps,
             roofline=dict(bound="tensor", kernel="gemm_tc_kernel (all tcgen05 GEMM launches of a step)", achieved=gemm_tf,
-                          peak=peaks["tf_sustained"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_sustained"], traffic=None,
+                          peak=peaks["tf_sustained"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_sustained"],
+                          traffic=traffic.get("gemm_dram_bytes_per_launch"),
+                          note="FP16X3 issues 3 tcgen05 MMAs per product: the tensor pipe does 3x the algorithmic FLOPs "
+                               "(achievable ceiling = peak / 3)", mma_frac=3 * gemm_tf / peaks["tf_sustained"] if args.precision == "fp16x3" else gemm_tf / peaks["tf_sustained"],
                           peak_source=peaks["source"] + " bf16 sustained",
                           launches_per_step=gemm["launches"] // prof_steps, share_of_step=gemm["ms"] / prof_steps / step_ms_prof,
                           whole_step_tflops=GFLOP_PER_PERSON_PASS * passes * B / (ms / args.steps * 1e-3) / 1e3),
-            decode_roofline=dict(bound="hbm", kernel="decode_kernel", achieved=dec_gbs, peak=peaks["hbm"], unit="GB/s",
-                                 frac=dec_gbs / peaks["hbm"], traffic=None, bytes_per_launch=dec_bytes,
-                                 us_per_launch=dec["ms"] / max(dec["launches"], 1) * 1e3,
-                                 share_of_step=dec["ms"] / prof_steps / step_ms_prof),
+            decode_roofline=None if dec256 is None else dict(bound="hbm", kernel="decode_kernel", workload="batch 256 model logits, no TTA (SURVEY 8d: 53.60 MB)",
+                                 achieved=dec256["plain"]["gbs"], peak=peaks["hbm"], unit="GB/s",
+                                 frac=dec256["plain"]["gbs"] / peaks["hbm"], traffic=traffic.get("decode_b256_dram_bytes"),
+                                 bytes_per_launch=dec256["plain"]["bytes"], us_per_launch=dec256["plain"]["us"],
+                                 tta=dict(achieved=dec256["tta"]["gbs"], frac=dec256["tta"]["gbs"] / peaks["hbm"],
+                                          bytes_per_launch=dec256["tta"]["bytes"], us_per_launch=dec256["tta"]["us"],
+                                          traffic=traffic.get("decode_b256_tta_dram_bytes")),
+                                 in_step=dict(batch=B, tta=flip, achieved=dec_gbs, frac=dec_gbs / peaks["hbm"], bytes_per_launch=dec_bytes,
+                                              us_per_launch=dec["ms"] / max(dec["launches"], 1) * 1e3,
+                                              share_of_step=dec["ms"] / prof_steps / step_ms_prof)),
             kernel_ms_per_step={k: prof[k]["ms"] / prof_steps for k in ("gemm", "attention", "decode", "other")},
         )
         if not args.no_cpu_baseline:

@@ -89,21 +89,24 @@ struct GemmCfg {
 };
 
 // erf by Abramowitz & Stegun 7.1.26 (|error| < 6e-7 in fp32, below the rounding noise of an fp32
-// GELU): branch-free, two MUFU ops, so the fc1 epilogue stays well under the tile's MMA time and the
+// GELU): branch-free, two MUFU ops, so the fc1 epilogue stays under the tile's MMA time and the
 // kernel stays inside the instruction cache.  (The CUDA-core verification GEMM keeps erff.)
+// Returns OUT_SCALE * gelu(v); the operand scale of the next GEMM rides along for free:
+// s * 0.5 v (1 + erf) = h + |h| E with h = 0.5 s v, E = erf(|x|) (x and h share their sign).
+template <int OUT_SCALE>
 __device__ __forceinline__ float gelu_fast(float v) {
-  const float x = v * 0.70710678118654752440f;
-  const float a = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  const float a = fabsf(v) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(a * a) * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((a * -1.4426950408889634f) * a));
   const float erf_abs = fmaf(-p, e, 1.0f);
-  return 0.5f * v * (1.0f + copysignf(erf_abs, x));
+  const float h = v * (0.5f * OUT_SCALE);
+  return fmaf(fabsf(h), erf_abs, h);
 }
 
 __device__ __forceinline__ void st_shared_f4(uint32_t addr, float4 v) {
@@ -120,21 +123,25 @@ __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {  // {lo, hi} -> f16x2, clamped to +-65504
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // Four consecutive columns of one operand row (col % 4 == 0), see common.cuh "GEMM operand formats";
-// rowk = row * k (element offset of the row in the LOGICAL (rows, k) matrix).
+// rowk = row * k (element offset of the row in the LOGICAL (rows, k) matrix).  FP16X3: v is already
+// in operand units (64x the value, folded into the epilogue's affine step).
 template <int PREC>
 __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int col, int k, float4 v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
-    v.x = fminf(fmaxf(v.x * kOpScale, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y * kOpScale, -65504.f), 65504.f);
-    v.z = fminf(fmaxf(v.z * kOpScale, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w * kOpScale, -65504.f), 65504.f);
-    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    uint2 hi, lo;
+    hi.x = pack_half2_sat(v.x, v.y); hi.y = pack_half2_sat(v.z, v.w);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
     const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y);
     const __half2 l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
-    __half* p = reinterpret_cast<__half*>(base) + 2 * rowk + col;
-    uint2 hi, lo;
-    hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
     lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+    __half* p = reinterpret_cast<__half*>(base) + 2 * rowk + col;
     *reinterpret_cast<uint2*>(p) = hi;
     *reinterpret_cast<uint2*>(p + k) = lo;
   } else if constexpr (PREC == PP_PREC_BF16) {
@@ -143,11 +150,8 @@ __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int
     o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + rowk + col) = o;
   } else {
-    v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
-    v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
-    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
     uint2 o;
-    o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+    o.x = pack_half2_sat(v.x, v.y); o.y = pack_half2_sat(v.z, v.w);
     *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + rowk + col) = o;
   }
 }
@@ -382,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               if (n < e.n) {
                 const float sc = (e.scale ? __ldg(e.scale + n) : 1.f) * acc_scale, sh = e.shift ? __ldg(e.shift + n) : 0.f;
                 float x = fmaf(v[c], sc, sh);
-                if (e.act == PP_ACT_GELU) x = gelu_fast(x);
+                if (e.act == PP_ACT_GELU) x = gelu_fast<1>(x);
                 if (e.act == PP_ACT_RELU) x = fmaxf(x, 0.f);
                 dbase[(int64_t)c * e.plane] = x;
               }
@@ -400,7 +404,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e.scale) sc = __ldg(reinterpret_cast<const float4*>(e.scale + col));
             if (e.shift) sh = __ldg(reinterpret_cast<const float4*>(e.shift + col));
-            sc.x *= acc_scale; sc.y *= acc_scale; sc.z *= acc_scale; sc.w *= acc_scale;
+            // FP16X3 operand output: the 64x operand scale is folded into the affine step, or (GELU,
+            // which does not commute with scaling) into the activation itself
+            constexpr bool kToUnits = OUT == PP_OUT_OPERAND && PREC == PP_PREC_FP16X3;
+            const float osc = (kToUnits && e.act != PP_ACT_GELU) ? kOpScale : 1.0f;
+            const float asc = acc_scale * osc;
+            sc.x *= asc; sc.y *= asc; sc.z *= asc; sc.w *= asc;
+            sh.x *= osc; sh.y *= osc; sh.z *= osc; sh.w *= osc;
             float4 x[8], rr[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -420,8 +430,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               x[i].z = fmaf(x[i].z, sc.z, sh.z); x[i].w = fmaf(x[i].w, sc.w, sh.w);
             }
             if (e.act == PP_ACT_GELU) {
+              constexpr int GS = kToUnits ? (int)kOpScale : 1;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { x[i].x = gelu_fast(x[i].x); x[i].y = gelu_fast(x[i].y); x[i].z = gelu_fast(x[i].z); x[i].w = gelu_fast(x[i].w); }
+              for (int i = 0; i < 8; ++i) { x[i].x = gelu_fast<GS>(x[i].x); x[i].y = gelu_fast<GS>(x[i].y); x[i].z = gelu_fast<GS>(x[i].z); x[i].w = gelu_fast<GS>(x[i].w); }
             } else if (e.act == PP_ACT_RELU) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) { x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f); }
@@ -450,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               for (int c = 0; c < 4 && col + c < e.n; ++c) {
                 const float sc = (e.scale ? __ldg(e.scale + col + c) : 1.f) * acc_scale, sh = e.shift ? __ldg(e.shift + col + c) : 0.f;
                 float x = fmaf(ld_shared_f1(src + 4 * c), sc, sh);
-                if (e.act == PP_ACT_GELU) x = gelu_fast(x);
+                if (e.act == PP_ACT_GELU) x = gelu_fast<1>(x);
                 if (e.act == PP_ACT_RELU) x = fmaxf(x, 0.f);
                 if constexpr (OUT == PP_OUT_F32) {
                   if (e.residual) x += e.residual[rrow * e.ldd + col + c];

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch the fused decode kernel a few times on one input family (for ncu captures).
 
-    python tools/decode_probe.py planted|noise1|synth [batch] [tta] [iters]
+    python tools/decode_probe.py planted|noise1|flat|planted_alt [batch] [tta] [iters]
 """
 import os
 import sys
@@ -16,6 +16,8 @@ from probpose_code_b200 import ops  # noqa: E402
 
 def main():
     fam = sys.argv[1] if len(sys.argv) > 1 else "planted"
+    fam_alt = fam.endswith("_alt")
+    fam = fam.replace("_alt", "")
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     tta = (sys.argv[3] if len(sys.argv) > 3 else "0") not in ("0", "false")
     iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
@@ -25,8 +27,14 @@ def main():
     z = torch.from_numpy(gen(1)).cuda()
     zf = torch.from_numpy(gen(2)).cuda() if tta else None
     fi = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]
-    for _ in range(iters):
-        ops.decode(z, zf, fi if tta else None, input_is_logits=True)
+    if fam_alt:
+        zf = torch.from_numpy(gen(2)).cuda()
+        for _ in range(iters):  # alternate plain / TTA launches (tools/ncu_traffic.py expects this order)
+            ops.decode(z, input_is_logits=True)
+            ops.decode(z, zf, fi, input_is_logits=True)
+    else:
+        for _ in range(iters):
+            ops.decode(z, zf, fi if tta else None, input_is_logits=True)
     torch.cuda.synchronize()
 
 
