@@ -150,6 +150,21 @@ PP_API int pp_operand_from_f32(int32_t precision, const float* src, int64_t rows
                         void* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Crop front-end: one frame + per-person forward affine matrices -> the uint8
+ * model inputs.  Replaces, per person on the host in the reference, TopdownAffine's
+ *   cv2.warpAffine(img, warp_mat, (w, h), flags=cv2.INTER_LINEAR)
+ * (mmpose/datasets/transforms/topdown_transforms.py:126) + PackPoseInputs' HWC -> CHW
+ * (mmpose/datasets/transforms/formatting.py), bit for bit (OpenCV's fixed-point bilinear warp,
+ * BORDER_CONSTANT 0).  warp_mats are the float32 matrices of get_udp_warp_matrix
+ * (mmpose/structures/bbox/transforms.py:315-359), computed by the caller as the reference does.
+ *  frame_hwc_bgr  device (frame_h, frame_w, 3) uint8, row pitch frame_row_bytes
+ *  warp_mats      device (n, 2, 3) fp32
+ *  crops          device (n, 3, out_h, out_w) uint8 BGR out (what pp_engine_infer consumes)
+ * ---------------------------------------------------------------------------------- */
+PP_API int pp_crop_warp(const uint8_t* frame_hwc_bgr, int32_t frame_h, int32_t frame_w, int64_t frame_row_bytes,
+                        const float* warp_mats, int32_t n, uint8_t* crops, int32_t out_h, int32_t out_w, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Engine: the whole forward (preprocess -> ViT -> ProbMapHead -> fused decode).
  * Replaces TopdownPoseEstimator.predict (mmpose/models/pose_estimators/topdown.py:86-126)
  * = PoseDataPreprocessor.forward (models/data_preprocessors/data_preprocessor.py:79-104)

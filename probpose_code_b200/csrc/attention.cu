@@ -56,6 +56,12 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_fast(float x) {  // 2^x, MUFU.EX2 (flushes denormal results: irrelevant after max-subtraction)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Two fp32 -> packed 16-bit pair (x in the low half), and the scaled residual pair for FP16X3.
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float x, float y) {
@@ -190,15 +196,16 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
       }
       c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1)); c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
       c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
-      const float r0 = exp2f((mx0 - c0) * c_exp), r1 = exp2f((mx1 - c1) * c_exp);  // exp2(-inf) = 0 on the first chunk
+      const float r0 = ex2_fast((mx0 - c0) * c_exp), r1 = ex2_fast((mx1 - c1) * c_exp);  // 2^-inf = 0 on the first chunk
       mx0 = c0; mx1 = c1;
       l0 *= r0; l1 *= r1;
 #pragma unroll
       for (int dt = 0; dt < DT; ++dt) { o0[dt][0] *= r0; o0[dt][1] *= r0; o0[dt][2] *= r1; o0[dt][3] *= r1; }
 #pragma unroll
       for (int nt = 0; nt < KTC; ++nt) {
-        s[nt][0] = exp2f(fmaf(s[nt][0] - mx0, c_exp, p_exp)); s[nt][1] = exp2f(fmaf(s[nt][1] - mx0, c_exp, p_exp));
-        s[nt][2] = exp2f(fmaf(s[nt][2] - mx1, c_exp, p_exp)); s[nt][3] = exp2f(fmaf(s[nt][3] - mx1, c_exp, p_exp));
+        // (s - max) first: exact for scores near the maximum, where the probabilities matter
+        s[nt][0] = ex2_fast(fmaf(s[nt][0] - mx0, c_exp, p_exp)); s[nt][1] = ex2_fast(fmaf(s[nt][1] - mx0, c_exp, p_exp));
+        s[nt][2] = ex2_fast(fmaf(s[nt][2] - mx1, c_exp, p_exp)); s[nt][3] = ex2_fast(fmaf(s[nt][3] - mx1, c_exp, p_exp));
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
       }

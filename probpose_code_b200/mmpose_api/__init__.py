@@ -8,6 +8,7 @@ from .backbone import VisionTransformer
 from .codec import BaseKeypointCodec, ProbMap
 from .estimator import PoseDataPreprocessor, TopdownPoseEstimator
 from .head import BaseHead, ProbMapHead
+from .inference import TopdownAffine, inference_topdown
 from .registry import HAVE_MMPOSE, KEYPOINT_CODECS, MODELS, Registry
 from .structures import InstanceData, PixelData, PoseDataSample
 

@@ -121,3 +121,25 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
     with torch.cuda.device(dev):
         check(lib().pp_gemm(C.byref(args), _stream()), "pp_gemm")
     return out
+
+
+def crop_warp(frame: torch.Tensor, warp_mats: torch.Tensor, out_hw=(256, 192), out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``pp_crop_warp``: frame uint8 BGR (H, W, 3) CUDA + forward affine matrices fp32 (N, 2, 3) CUDA ->
+    crops uint8 BGR (N, 3, h, w), bit-identical to ``cv2.warpAffine(..., flags=cv2.INTER_LINEAR)`` per person
+    followed by HWC -> CHW (topdown_transforms.py:126, formatting.py)."""
+    _need_cuda(frame, "frame", torch.uint8)
+    _need_cuda(warp_mats, "warp_mats", torch.float32)
+    if frame.dim() != 3 or frame.shape[2] != 3:
+        raise ValueError(f"frame must be (H, W, 3) uint8 BGR, got {tuple(frame.shape)}")
+    if warp_mats.dim() != 3 or tuple(warp_mats.shape[1:]) != (2, 3):
+        raise ValueError(f"warp_mats must be (N, 2, 3), got {tuple(warp_mats.shape)}")
+    n, (h, w) = warp_mats.shape[0], out_hw
+    crops = out if out is not None else torch.empty((n, 3, h, w), dtype=torch.uint8, device=frame.device)
+    if out is not None:
+        _need_cuda(out, "out", torch.uint8)
+        if tuple(out.shape) != (n, 3, h, w):
+            raise ValueError(f"out must be {(n, 3, h, w)}")
+    with torch.cuda.device(frame.device):
+        check(lib().pp_crop_warp(frame.data_ptr(), frame.shape[0], frame.shape[1], frame.stride(0), warp_mats.data_ptr(), n,
+                                 crops.data_ptr(), h, w, _stream()), "pp_crop_warp")
+    return crops
