@@ -96,6 +96,8 @@ attention_mma_kernel(const uint16_t* __restrict__ qkv_op, int heads, uint16_t* _
   static_assert(NTOK % 16 == 0 && DH % 16 == 0, "tile shapes");
 
   extern __shared__ __align__(16) uint8_t att_smem[];  // [K hi | K lo | V hi | V lo]
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int D = heads * DH;
   const int RS = NOPS * 3 * D;  // qkv operand row stride (elements)
@@ -281,8 +283,8 @@ int launch_mma(const void* qkv_op, int batch, int heads, void* out_op, cudaStrea
     PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  kern<<<batch * heads, kAttThreads, SMEM, st>>>(reinterpret_cast<const uint16_t*>(qkv_op), heads,
-                                                  reinterpret_cast<uint16_t*>(out_op));
+  PP_CHECK_CUDA(launch_pdl(kern, dim3(batch * heads), dim3(kAttThreads), SMEM, st, reinterpret_cast<const uint16_t*>(qkv_op), heads,
+                           reinterpret_cast<uint16_t*>(out_op)));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;

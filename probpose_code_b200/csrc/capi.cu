@@ -8,6 +8,11 @@ namespace pp {
 static thread_local char g_error[1024] = "";
 thread_local int64_t g_launch_count = 0;
 
+bool pdl_enabled() {
+  static const bool on = getenv("PP_NO_PDL") == nullptr;
+  return on;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "../../include/probpose_b200.h"
 
@@ -37,6 +39,28 @@ extern thread_local int64_t g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 constexpr int kWarp = 32;
+
+// ---- programmatic dependent launch -------------------------------------------------------
+// Every kernel of the step is launched with programmatic stream serialization: it may start (barrier
+// init, TMEM allocation, descriptor prefetch) while the previous kernel drains, and blocks in
+// pdl_wait() until that kernel has completed and its writes are visible.  pdl_wait() must precede the
+// first access to any global memory another kernel of the stream writes or still reads.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // capi.cu: on unless PP_NO_PDL is set in the environment
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -717,6 +717,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const __grid_con
   const int per = p.count / gridDim.x, rem = p.count % gridDim.x;
   const int first = blockIdx.x * per + min((int)blockIdx.x, rem);
   const int cnt = per + ((int)blockIdx.x < rem ? 1 : 0);
+  pdl_launch_dependents();
   if (threadIdx.x == 0) { sm.q_count = 0; sm.next = 0; sm.all_done = 0; }
   for (int i = threadIdx.x; i < PP_MAX_KEYPOINTS * (kTaps + 1); i += kDecThreads) (&sm.taps[0][0])[i] = (&p.taps[0][0])[i];
   if (lane == 0) {
@@ -725,6 +726,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();  // the logits / scalars come from the previous kernels of the stream
   const bool tta = p.maps_flip != nullptr;
   uint32_t phase = 0;
 
@@ -861,7 +863,7 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
   // one persistent CTA per SM; with few maps, enough CTAs that every warp has one
   const int64_t want = (count + kDecWarps - 1) / kDecWarps;
   const int grid = (int)(want < sms ? want : sms);
-  kern<<<grid, kDecThreads, sizeof(DecodeSmem), (cudaStream_t)stream>>>(p);
+  PP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDecThreads), sizeof(DecodeSmem), (cudaStream_t)stream, p));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;

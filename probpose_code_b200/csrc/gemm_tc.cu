@@ -181,6 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   auto stage_b = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::A_BYTES + part * Cfg::B_BYTES; };
 
   constexpr int BK = Cfg::BK;
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = K / BK;
   const int num_tiles = num_m_tiles * num_n_tiles;
@@ -216,6 +217,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if constexpr (PAIR) ptx::cluster_sync(); else __syncthreads();  // barriers + TMEM visible (pair: in both CTAs)
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above overlapped the previous kernel's tail; operands, residuals and outputs are only
+  // touched after it has completed
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -576,17 +580,24 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams&
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (PAIR) {  // one cluster of 2 CTAs (one TPC) per 256-row tile, as many clusters as fit the SMs
     const int64_t pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   } else {
     cfg.gridDim = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
   }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
   const int k = a.k;
   PP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tma, tmw, k, mt, nt, tp, e));
   count_launch();

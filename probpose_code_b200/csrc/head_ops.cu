@@ -12,6 +12,8 @@ namespace pp {
 // Works on 16-byte chunks of the operand planes (FP16X3 rows are [hi plane | lo plane]).
 __global__ void __launch_bounds__(256) gather_taps_kernel(const GatherParams p, int planes, int eb, const uint8_t* src,
                                                           uint8_t* dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cpc = p.c * eb / 16;  // chunks per (tap, plane)
   const int64_t per_row = (int64_t)planes * p.ntaps * cpc;
   const int64_t total = (int64_t)p.batch * p.h * p.w * per_row;
@@ -45,8 +47,8 @@ int launch_gather_taps(int prec, const GatherParams& p, const void* src_op, void
   const int64_t total = (int64_t)p.batch * p.h * p.w * planes * p.ntaps * (p.c * eb / 16);
   if (total == 0) return PP_OK;
   const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  gather_taps_kernel<<<grid, 256, 0, st>>>(p, planes, eb, reinterpret_cast<const uint8_t*>(src_op),
-                                           reinterpret_cast<uint8_t*>(dst_op));
+  PP_CHECK_CUDA(launch_pdl(gather_taps_kernel, dim3(grid), dim3(256), 0, st, p, planes, eb, reinterpret_cast<const uint8_t*>(src_op),
+                           reinterpret_cast<uint8_t*>(dst_op)));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
@@ -56,6 +58,8 @@ int launch_gather_taps(int prec, const GatherParams& p, const void* src_op, void
 template <int PREC>
 __global__ void __launch_bounds__(256) pool_relu_kernel(const float* __restrict__ x, int batch, int h, int w, int c, int ph,
                                                         int pw, void* out_op) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int oh = h / ph, ow = w / pw, c4 = c / 4;
   const int64_t total = (int64_t)batch * oh * ow * c4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -80,7 +84,7 @@ int launch_pool_relu(int prec, const float* x, int batch, int h, int w, int c, i
   const int64_t total = (int64_t)batch * (h / ph) * (w / pw) * (c / 4);
   if (total == 0) return PP_OK;
   const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  PP_DISPATCH_PREC(prec, (pool_relu_kernel<PREC><<<grid, 256, 0, st>>>(x, batch, h, w, c, ph, pw, out_op)));
+  { cudaError_t lerr = cudaSuccess; PP_DISPATCH_PREC(prec, (lerr = launch_pdl(pool_relu_kernel<PREC>, dim3(grid), dim3(256), 0, st, x, batch, h, w, c, ph, pw, out_op))); PP_CHECK_CUDA(lerr); }
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
@@ -93,6 +97,8 @@ __global__ void __launch_bounds__(256) branch_tail_kernel(const float* __restric
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           float* scalars) {
   extern __shared__ float pooled[];  // 4 * c
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, C4 = 4 * c;
   const float* xb = x + (size_t)b * 4 * C4;
   for (int i = threadIdx.x; i < C4; i += blockDim.x)
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(256) branch_tail_kernel(const float* __restric
 int launch_branch_tail(const float* x, int batch, int c, int k, const float* w, const float* bias, float* scalars,
                        cudaStream_t st) {
   if (batch == 0) return PP_OK;
-  branch_tail_kernel<<<batch, 256, (size_t)4 * c * sizeof(float), st>>>(x, c, k, w, bias, scalars);
+  PP_CHECK_CUDA(launch_pdl(branch_tail_kernel, dim3(batch), dim3(256), (size_t)4 * c * sizeof(float), st, x, c, k, w, bias, scalars));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;

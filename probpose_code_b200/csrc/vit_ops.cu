@@ -13,6 +13,8 @@ namespace pp {
 // ---- patch extraction --------------------------------------------------------------------
 template <int PREC>
 __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyParams p, void* a_op) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int P = p.patch, PP = P * P, K = 3 * PP, K4 = K / 4;
   const int tokens = p.gh * p.gw;
   const int64_t total = (int64_t)p.passes * p.batch * tokens * K4;
@@ -52,7 +54,7 @@ int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t 
   const int64_t total = (int64_t)p.passes * p.batch * p.gh * p.gw * (3 * p.patch * p.patch / 4);
   if (total == 0) return PP_OK;
   const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-  PP_DISPATCH_PREC(prec, (patchify_kernel<PREC><<<grid, 256, 0, st>>>(p, a_op)));
+  { cudaError_t lerr = cudaSuccess; PP_DISPATCH_PREC(prec, (lerr = launch_pdl(patchify_kernel<PREC>, dim3(grid), dim3(256), 0, st, p, a_op))); PP_CHECK_CUDA(lerr); }
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float eps, int64_t rows,
                                                         void* out_op, float* out_f32, int pad_gh, int pad_gw) {
   constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -116,9 +120,9 @@ int launch_layernorm(int prec, const float* x, const float* gamma, const float* 
   if (rows == 0) return PP_OK;
   const int grid = (int)((rows + 7) / 8);
   if (d == 384) {
-    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 3><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32, pad_gh, pad_gw)));
+    { cudaError_t lerr = cudaSuccess; PP_DISPATCH_PREC(prec, (lerr = launch_pdl(layernorm_kernel<PREC, 3>, dim3(grid), dim3(256), 0, st, x, gamma, beta, eps, rows, out_op, out_f32, pad_gh, pad_gw))); PP_CHECK_CUDA(lerr); }
   } else {
-    PP_DISPATCH_PREC(prec, (layernorm_kernel<PREC, 6><<<grid, 256, 0, st>>>(x, gamma, beta, eps, rows, out_op, out_f32, pad_gh, pad_gw)));
+    { cudaError_t lerr = cudaSuccess; PP_DISPATCH_PREC(prec, (lerr = launch_pdl(layernorm_kernel<PREC, 6>, dim3(grid), dim3(256), 0, st, x, gamma, beta, eps, rows, out_op, out_f32, pad_gh, pad_gw))); PP_CHECK_CUDA(lerr); }
   }
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
