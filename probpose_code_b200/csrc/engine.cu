@@ -61,6 +61,11 @@ struct pp_engine {
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
   double prof_gemm_flops = 0;
+  // the four scalar branches are independent after the shared first convolution: their small
+  // pooled-stage convolutions run concurrently on side streams (fork / join by events)
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  size_t g_stride = 0;  // bytes between the per-branch tap-gather buffers
 
   // packed weights (byte offsets)
   size_t w_patch;
@@ -192,7 +197,8 @@ static size_t plan(pp_engine* e) {
   e->feat_bytes = pp_operand_bytes(prec, Mp0, D);
   e->feat_f32 = b.take((size_t)M * D * sizeof(float));
   if (DC > 0) {
-    e->g_op = b.take(pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 9 * D));  // tap gather of the pooled 4x4 / 2x2 stages
+    e->g_stride = (pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 9 * D) + 1023) & ~size_t(1023);
+    e->g_op = b.take(4 * e->g_stride);  // tap gathers of the pooled 4x4 / 2x2 stages, one buffer per branch
     e->d1_op = b.take(pp_operand_bytes(prec, Mp1, DC));
     e->d1_bytes = pp_operand_bytes(prec, Mp1, DC);
     e->d2_op = b.take(pp_operand_bytes(prec, 16 * M, DC));
@@ -387,13 +393,21 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
                             e->at<>(e->pool_op), st); }));
     h /= pool[j - 1][0]; w /= pool[j - 1][1];
     const int64_t rows = (int64_t)n_img * h * w;
+    if (e->fork_ev) PP_CHECK_CUDA(cudaEventRecord(e->fork_ev, st));
     for (int br = 0; br < 4; ++br) {
+      cudaStream_t bs = (br == 0 || !e->fork_ev) ? st : e->side[br - 1];
+      if (bs != st) PP_CHECK_CUDA(cudaStreamWaitEvent(bs, e->fork_ev, 0));
+      void* gbuf = e->at<>(e->g_op + br * e->g_stride);
       g3.h = h; g3.w = w; g3.src_c = 4 * D; g3.c_off = br * D;
-      PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_gather_taps(prec, g3, e->at<>(e->pool_op), e->at<>(e->g_op), st); }));
-      pp_gemm_args g = gemm_args(e, rows, D, 9 * D, e->at<>(e->g_op), e->at<>(j == 1 ? e->w_c2[br] : e->w_c3[br]));
+      PP_TRY(timed(e, PP_KC_OTHER, bs, [&] { return launch_gather_taps(prec, g3, e->at<>(e->pool_op), gbuf, bs); }));
+      pp_gemm_args g = gemm_args(e, rows, D, 9 * D, gbuf, e->at<>(j == 1 ? e->w_c2[br] : e->w_c3[br]));
       g.scale = e->at<float>(e->c_scale[j]) + br * D; g.shift = e->at<float>(e->c_shift[j]) + br * D;
       g.ldd = 4 * D; g.d = e->at<float>(e->c_f32) + br * D;
-      PP_TRY(gemm(e, g, st));
+      PP_TRY(gemm(e, g, bs));
+      if (bs != st) {
+        PP_CHECK_CUDA(cudaEventRecord(e->join_ev[br - 1], bs));
+        PP_CHECK_CUDA(cudaStreamWaitEvent(st, e->join_ev[br - 1], 0));
+      }
     }
   }
   PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_branch_tail(e->at<float>(e->c_f32), n_img, D, K, e->at<float>(e->tail_w), e->at<float>(e->tail_b), scalars, st); }));
@@ -435,6 +449,17 @@ extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_
   }
   e->base = reinterpret_cast<uint8_t*>(workspace);
   e->bytes = workspace_bytes;
+  if (e->DC > 0 && getenv("PP_NO_BRANCH_STREAMS") == nullptr) {  // side streams of the scalar branches (no device memory involved)
+    bool ok = cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("pp_engine_create: could not create the branch streams: %s", cudaGetErrorString(cudaGetLastError()));
+      pp_engine_destroy(e);
+      return PP_ERR_CUDA;
+    }
+  }
   *out = e;
   return PP_OK;
 }
@@ -443,6 +468,11 @@ extern "C" void pp_engine_destroy(pp_engine* e) {
   if (!e) return;
   for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
+  if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+  for (int i = 0; i < 3; ++i) {
+    if (e->join_ev[i]) cudaEventDestroy(e->join_ev[i]);
+    if (e->side[i]) cudaStreamDestroy(e->side[i]);
+  }
   delete e;
 }
 

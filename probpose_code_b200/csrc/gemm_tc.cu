@@ -672,9 +672,17 @@ int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaSt
     // few rows (the pooled 4x4 / 2x2 stages of the scalar branches): narrower tiles spread the long
     // K loop over more SMs - with fewer tiles than SMs the time is K / 16 x 3 x BN / 2 cycles per tile
     const int64_t mt = (a.m + kBM - 1) / kBM;
-    const int widths[3] = {128, 64, 32};
-    for (int i = 0; i < 3 && mt * ((a.n + bn - 1) / bn) < num_sms(); ++i)
-      if (widths[i] < bn) bn = widths[i];
+    if (mt * ((a.n + bn - 1) / bn) < num_sms()) {
+      // cost model: rounds over the SMs x tile time (an MMA narrower than ~48 columns is latency-bound)
+      const int widths[3] = {128, 64, 32};
+      int64_t best_cost = -1;
+      for (int i = 0; i < 3; ++i) {
+        if (widths[i] > bn) continue;
+        const int64_t tiles = mt * ((a.n + widths[i] - 1) / widths[i]);
+        const int64_t cost = ((tiles + num_sms() - 1) / num_sms()) * (widths[i] > 48 ? widths[i] : 48);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = widths[i]; }
+      }
+    }
   }
   const int accs = (a.precision == PP_PREC_FP16X3 && a.k > kTwoAccMinK && bn <= 128) ? 2 : 1;
   // CTA pairs pay off once there are enough 256-row tiles to occupy the 74 TPCs
