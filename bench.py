@@ -76,9 +76,14 @@ def decode_leg(eng, dev, fi, batch: int = 256, sets: int = 4, iters: int = 40) -
             parts_f.append(eng.head(eng.backbone(x.flip(-1).contiguous()))[0])
         zs.append(torch.cat(parts).contiguous())
         zfs.append(torch.cat(parts_f).contiguous())
+    ps, pfs = [], []
+    for s_ in range(sets):  # trained-model-like planted peaks (second input family)
+        a_, b_ = synth.planted_logit_pair(batch, seed=7000 + s_, device=dev)
+        ps.append(a_)
+        pfs.append(b_)
     rec = torch.empty((batch, 17, 7), dtype=torch.float32, device=dev)
     out = {}
-    for name, tta in (("plain", False), ("tta", True)):
+    for name, tta, zs, zfs in (("plain", False, zs, zfs), ("tta", True, zs, zfs), ("planted_plain", False, ps, pfs), ("planted_tta", True, ps, pfs)):
         def run(i):
             if tta:
                 ops.decode(zs[i % sets], zfs[i % sets], fi, input_is_logits=True, out=rec)
@@ -363,6 +368,11 @@ def main():
                                  tta=dict(achieved=dec256["tta"]["gbs"], frac=dec256["tta"]["gbs"] / peaks["hbm"],
                                           bytes_per_launch=dec256["tta"]["bytes"], us_per_launch=dec256["tta"]["us"],
                                           traffic=traffic.get("decode_b256_tta_dram_bytes")),
+                                 planted=dict(workload="batch 256 planted-peak logits (trained-model-like, SURVEY 8d config 3)",
+                                              achieved=dec256["planted_plain"]["gbs"], frac=dec256["planted_plain"]["gbs"] / peaks["hbm"],
+                                              us_per_launch=dec256["planted_plain"]["us"],
+                                              tta=dict(achieved=dec256["planted_tta"]["gbs"], frac=dec256["planted_tta"]["gbs"] / peaks["hbm"],
+                                                       us_per_launch=dec256["planted_tta"]["us"])),
                                  in_step=dict(batch=B, tta=flip, achieved=dec_gbs, frac=dec_gbs / peaks["hbm"], bytes_per_launch=dec_bytes,
                                               us_per_launch=dec["ms"] / max(dec["launches"], 1) * 1e3,
                                               share_of_step=dec["ms"] / prof_steps / step_ms_prof)),

@@ -27,6 +27,18 @@ def planted_peak_logits(batch: int, seed: int = 0, amp=(2.0, 8.0), sigma=(1.0, 3
     return z.astype(np.float32)
 
 
+def planted_peak_pair(batch: int, seed: int = 0, flip_indices=(0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15),
+                      jitter: float = 0.05):
+    """A flip-TTA pair like a real model produces: the flipped pass sees the mirrored image, so its map
+    for keypoint flip_idx[k] is (up to noise) the mirror image of the plain pass's map for keypoint k.
+    Returns (logits, logits_flipped_pass)."""
+    z = planted_peak_logits(batch, seed)
+    rng = np.random.default_rng(seed + 7919)
+    inv = np.argsort(np.asarray(flip_indices))
+    zf = z[:, inv][..., ::-1] * rng.uniform(0.9, 1.1, (batch, K, 1, 1)) + rng.normal(0, jitter, z.shape)
+    return z, np.ascontiguousarray(zf.astype(np.float32))
+
+
 def noise_logits(batch: int, seed: int, std: float):
     """Flat / random-init regime: logits ~ N(0, std)."""
     rng = np.random.default_rng(seed)

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libprobpose_b200.so")
+LIB_PATH = os.environ.get("PROBPOSE_B200_LIB") or os.path.join(HERE, "libprobpose_b200.so")  # override: kernel-variant experiments
 
 PREC_FP16X3, PREC_BF16, PREC_FP16, PREC_FP32_SIMT = 0, 1, 2, 3
 PRECISIONS = {"fp16x3": PREC_FP16X3, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp32_simt": PREC_FP32_SIMT}

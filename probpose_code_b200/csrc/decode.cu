@@ -9,22 +9,24 @@
 // Reference semantics: probmap_head.py:641-645,757-798, tta.py:35-39,
 // post_processing.py:13-39,308-430 (see include/probpose_b200.h: pp_decode).
 //
-// HBM-bound by design: every map (12 KB, 24 KB with TTA) is read exactly once; the only global
-// write is the 28-byte record.  One persistent CTA per SM, 16 warps, ONE WARP PER MAP:
-//   * one lane issues a 12 KB bulk async copy (TMA, cp.async.bulk, completion on the warp's own
-//     mbarrier) of the map into the warp's private shared-memory tile; 16 x 12 KB per SM are in
-//     flight, and the next map and the flipped pass are prefetched into L2 meanwhile,
-//   * max -> candidate set {z > max - T} compacted with ballots into a short list (a trained head
-//     leaves 2-3 pixels) -> Michelot's fixed point on the list = the exact
-//     sort / cumsum threshold of sparsemax,
-//   * the convolution is evaluated sparsely: every support pixel adds w * g(dy) g(dx) (incl. its
-//     reflections) into the warp's private 64 x 48 shared-memory tile; the arg max is searched only
-//     over the rows of the support's bounding box (the OKS kernel is non-negative and decreasing,
-//     so the maximum of C cannot lie outside it),
-//   * all reductions are warp shuffles: no block barrier on this path.
+// HBM-bound by design: every map (12 KB, 24 KB with TTA) is read exactly once from HBM; the only
+// global write is the 28-byte record.  ONE WARP PER MAP, 8 maps per CTA, 2 CTAs (16 warps) per SM; no map
+// is staged in shared memory:
+//   * the warp streams its map through registers (24 coalesced 128-bit loads per lane, issued in
+//     chunks of 6; only the maximum of each float4 is kept),
+//   * max (CREDUX) -> candidate set {z > max - T}: the few float4 that hold a candidate are re-read
+//     (L1 / L2 hits) and ballot-compacted into a short list (a trained head leaves 2-3 pixels, see
+//     SURVEY.md 8c) -> Michelot's fixed point on the list = the exact sort / cumsum threshold of
+//     sparsemax,
+//   * the convolution is evaluated sparsely, C(q) = sum_s w_s g(dy) g(dx) (+ reflected images), only
+//     where the arg max can be - inside the support's bounding box (the OKS kernel is non-negative and
+//     decreasing, so the maximum of C cannot lie outside it): directly at the pixels of a compact box,
+//     or - scattered supports - by scattering every source's window into the warp's
+//     64 x 48 shared-memory tile and scanning the rows of the box,
+//   * all reductions are warp shuffles / redux: no block barrier on this path.
 // Maps that are not sparse (flat random-init logits, arbitrary / negative heatmaps handed to the
-// public codec API) are queued and handled by the whole CTA with a dense separable convolution
-// (decode_dense) between batches of sparse maps - correct for any input, just not HBM-bound.
+// public codec API) are queued and decoded afterwards by the whole CTA with a dense separable
+// convolution (decode_dense) - correct for any input, just not HBM-bound.
 #include "common.cuh"
 
 #include <math.h>
@@ -33,14 +35,14 @@ namespace pp {
 
 constexpr int kMaxRadius = 9;  // ceil(3 * 3.0): the variance is clipped to <= 3.0
 constexpr int kTaps = 2 * kMaxRadius + 1;
-constexpr int kDecWarps = 16;
+constexpr int kDecWarps = 8;    // maps per CTA (one warp each)
 constexpr int kDecThreads = 32 * kDecWarps;
-constexpr int kDenseWarps = 8;   // warps that run the dense path (3 float4 of the map per thread)
+constexpr int kDecCtasPerSm = 2;  // 16 maps in flight per SM
+constexpr int kDenseWarps = kDecWarps;   // the dense path uses the whole CTA (3 float4 of the map per thread)
 constexpr int kDenseThreads = 32 * kDenseWarps;
 constexpr int kListCap = 128;   // candidates per map kept in the compact list
 constexpr int kSrcCap = 2 * kListCap;
-constexpr int kQueueThresh = 16;  // deferred (dense) maps that trigger a cooperative pass
-constexpr int kQueueCap = kQueueThresh + 2 * kDecWarps;  // every warp may still deliver its current and its prefetched map
+constexpr int kBoxPix = 192;    // bounding boxes up to this area are evaluated pixel by pixel
 
 struct DecodeParams {
   const float* maps;
@@ -322,87 +324,79 @@ __device__ __noinline__ void decode_dense(const DecodeParams& p, int item, float
 }
 
 // =================================================================================================
-// Sparse path: one warp per map.
+// Sparse path: one warp per map, the map streamed from global memory straight into registers.
 // =================================================================================================
-struct __align__(16) WarpScratch {
-  float tile[64 * 48];          // the raw map while it is sparsified, then the convolved map C
-                                // (only the rows around the support are valid)
-  float val[kSrcCap];           // candidate / source values
-  unsigned short idx[kSrcCap];  // flat pixel index of each candidate / source
-  float fac[kTaps + 1];         // weight * row factors of the source being accumulated
-  unsigned long long bar;       // mbarrier of the bulk copies into `tile`
+struct __align__(16) WarpList {
+  float val[kSrcCap];            // candidate / source values
+  unsigned short idx[kSrcCap];   // flat pixel index, later (y << 8 | x), of each candidate / source
+  float taps[kTaps + 1];         // the map's OKS taps (zero-padded)
+  float fac[kTaps + 1];          // weight * row factors of the source being scattered
 };
 
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), m = (uint32_t)__cvta_generic_to_shared(bar);
-  // earlier generic-proxy accesses of the tile are ordered before the async-proxy write
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(m) : "memory");
-}
-__device__ __forceinline__ void bulk_wait(unsigned long long* bar, uint32_t parity) {
-  const uint32_t m = (uint32_t)__cvta_generic_to_shared(bar);
-  uint32_t ok = 0, spins = 0;
-  while (!ok) {
-    if (++spins > (1u << 24)) __trap();  // a lost copy must surface as an error, never hang the GPU
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok) : "r"(m), "r"(parity) : "memory");
-  }
+__device__ __forceinline__ float warp_max_fast(float v) {  // CREDUX.MAX.F32 (sm_100a)
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
-
-// Waits for the map in the warp's tile and compacts its candidates - logits: {z > max - T}, a superset
-// of the sparsemax support; heatmaps: the positive pixels - into the list (idx, raw val) at
-// list[off...].  Returns the number of entries, or -1 when the map is not sparse enough for this
-// path (too many candidates, or negative heatmap values).  `mx` returns the maximum (logits).
-// After the trailing __syncwarp the tile is free again.
-template <int H, int W>
-__device__ __forceinline__ int warp_compact(const DecodeParams& p, WarpScratch& ws, int off, int lane, uint32_t& phase,
-                                            float& mx) {
+// Streams one map (H x W fp32, 12 KB) through the warp's registers - 24 coalesced 128-bit loads per
+// lane, only the maximum of every float4 is kept.  Returns the lane's mask of float4 that hold a
+// candidate - logits: {z > max - T}, a superset of the sparsemax support; heatmaps: the positive
+// pixels - the candidate threshold in `thr` and the maximum in `mx` (logits).  `bad` is set when the
+// map has negative heatmap values (not a case for the sparse path).
+template <int H, int W, bool LOGITS>
+__device__ __forceinline__ unsigned warp_stream(const DecodeParams& p, const float* gmap, int lane, float& mx, float& thr,
+                                                bool& bad) {
   constexpr int NV = H * W / 128;  // float4 per lane
-  bulk_wait(&ws.bar, phase);
-  phase ^= 1u;
-  const float4* t4 = reinterpret_cast<const float4*>(ws.tile);
-  const unsigned lt_mask = (1u << lane) - 1u;
-  // one pass over the tile: per-float4 maxima stay in registers, so the candidate mask needs no re-read
+  constexpr int CH = 6;            // loads in flight per lane and chunk
+  static_assert(NV % CH == 0 && NV <= 32, "map must split into whole chunks of float4 per lane");
+  const float4* g4 = reinterpret_cast<const float4*>(gmap) + lane;
   float m4[NV];
   float lo = 0.f;
   mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const float4 q = t4[lane + 32 * j];
-    m4[j] = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
-    mx = fmaxf(mx, m4[j]);
-    if (!p.is_logits) lo = fminf(lo, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
+  for (int c = 0; c < NV; c += CH) {
+    float4 q[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) q[i] = __ldg(g4 + 32 * (c + i));
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      m4[c + i] = fmaxf(fmaxf(q[i].x, q[i].y), fmaxf(q[i].z, q[i].w));
+      if (!LOGITS) lo = fminf(fminf(lo, q[i].x), fminf(fminf(q[i].y, q[i].z), q[i].w));
+    }
   }
-  float thr = 0.f;
-  if (p.is_logits) {
-    mx = warp_max(mx);
+#pragma unroll
+  for (int j = 0; j < NV; j += 2) mx = fmaxf(mx, fmaxf(m4[j], m4[j + 1]));
+  thr = 0.f;
+  bad = false;
+  if (LOGITS) {
+    mx = warp_max_fast(mx);
     // candidates: z / T > max / T - 1.  The raw-domain test is made slightly generous (any superset
     // of the support gives the same threshold); the exact scaled values are formed per candidate.
     thr = mx - p.temperature * 1.000001f - 1e-30f;
-  } else if (__any_sync(0xffffffffu, lo < 0.f)) {
+  } else {
     // negative values break the "maximum lies inside the support's bounding box" argument
-    __syncwarp();
-    return -1;
+    bad = __any_sync(0xffffffffu, lo < 0.f);
   }
-  unsigned jm = 0;
+  unsigned bits = 0;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) jm |= (m4[j] > thr ? 1u : 0u) << j;
-  jm = __reduce_or_sync(0xffffffffu, jm);
-  // ballot compaction of {e > thr} for the few float4 columns that hold a candidate
+  for (int j = 0; j < NV; ++j) bits |= (m4[j] > thr ? 1u : 0u) << j;
+  return bits;
+}
+
+// Compacts the candidates of a streamed map into the list (idx, raw val) at list[off...]: in rounds,
+// every lane re-reads its next float4 that holds a candidate (L1 / L2 hits); ballot compaction keeps
+// the list order deterministic (round, component, lane).  Returns the number of entries, or -1 when
+// there are too many for this path.
+__device__ __forceinline__ int warp_compact(const float* gmap, unsigned bits, float thr, WarpList& wl, int off, int lane) {
+  const float4* g4 = reinterpret_cast<const float4*>(gmap) + lane;
+  const unsigned lt_mask = (1u << lane) - 1u;
   int n = 0;
-  while (jm) {
-    const int j = __ffs(jm) - 1;
-    jm &= jm - 1;
-    const float4 q = t4[lane + 32 * j];
+  while (__any_sync(0xffffffffu, bits != 0u)) {
+    const int j = __ffs(bits) - 1;
+    float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (bits) q = __ldg(g4 + 32 * j);
+    bits &= bits - 1u;
     const float e[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -412,8 +406,8 @@ __device__ __forceinline__ int warp_compact(const DecodeParams& p, WarpScratch& 
       if (n + add <= kListCap) {  // warp-uniform; on overflow only the count keeps growing
         if (take) {
           const int pos = off + n + __popc(bal & lt_mask);
-          ws.val[pos] = e[c];
-          ws.idx[pos] = (unsigned short)((lane + 32 * j) * 4 + c);
+          wl.val[pos] = e[c];
+          wl.idx[pos] = (unsigned short)((lane + 32 * j) * 4 + c);
         }
       }
       n += add;
@@ -426,15 +420,15 @@ __device__ __forceinline__ int warp_compact(const DecodeParams& p, WarpScratch& 
 
 // List entries (pixel index, raw value) -> (y << 8 | x, heatmap value): sparsemax threshold by
 // Michelot's fixed point on the list (logits), mirror of the flipped pass.
-template <int H, int W>
-__device__ __forceinline__ void warp_finish_list(const DecodeParams& p, WarpScratch& ws, int off, int n, int mirror, float mx,
+template <int H, int W, bool LOGITS>
+__device__ __forceinline__ void warp_finish_list(const DecodeParams& p, WarpList& ws, int off, int n, int mirror, float mx,
                                                  int lane) {
   for (int i = lane; i < n; i += 32) {
     const int px = ws.idx[off + i];
     const int y = px / W, x = px % W;
     ws.idx[off + i] = (unsigned short)((y << 8) | (mirror ? W - 1 - x : x));
   }
-  if (p.is_logits) {
+  if (LOGITS) {
     // tau <- (sum_{z > tau} z - 1) / #{z > tau} until the set stops shrinking = the sort / cumsum
     // threshold of Martins & Astudillo, Alg. 1 (on z - max z).
     const float mxs = p.temp_is_pow2 ? mx * p.inv_temperature : mx / p.temperature;
@@ -481,28 +475,38 @@ __device__ __forceinline__ void warp_finish_list(const DecodeParams& p, WarpScra
   __syncwarp();
 }
 
-// The sparse decode of one map whose first pass sits (or is arriving) in the warp's tile.
-// `issue_next` starts the bulk copy of the warp's next map as soon as the tile is free for it.
-// Returns false when the map has to go through the dense path.
-template <int H, int W, typename IssueNext>
-__device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, WarpScratch& ws, const float (*s_taps)[kTaps + 1],
-                                              int lane, uint32_t& phase, IssueNext&& issue_next) {
+// The sparse decode of one map.  Returns false when the map has to go through the dense path.
+template <int H, int W, bool LOGITS>
+__device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, WarpList& ws, int lane, float* tile) {
   constexpr int NPX = H * W;
   const int K = p.num_kpts;
   const int b = item / K, k = item % K;
   const bool tta = p.maps_flip != nullptr;
   const int kf = tta ? p.flip_idx[k] : k;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float* map1 = p.maps + (size_t)item * NPX;
+  const float* map2 = tta ? p.maps_flip + (size_t)(b * K + kf) * NPX : nullptr;
+  const int rad = p.radius[k];
+  if (lane < kTaps + 1) ws.taps[lane] = p.taps[k][lane];  // read after the __syncwarp()s of the list stages
 
-  float mx1, mx2 = 0.f;
-  const int n1 = warp_compact<H, W>(p, ws, 0, lane, phase, mx1);
-  if (n1 < 0) { issue_next(); return false; }
+  float mx1, mx2 = 0.f, thr1, thr2 = 0.f;
+  bool bad1, bad2 = false;
+  const unsigned bits1 = warp_stream<H, W, LOGITS>(p, map1, lane, mx1, thr1, bad1);
+  unsigned bits2 = 0;
+  if (tta) bits2 = warp_stream<H, W, LOGITS>(p, map2, lane, mx2, thr2, bad2);
+  if (bad1 || bad2) return false;
+
+  const int n1 = warp_compact(map1, bits1, thr1, ws, 0, lane);
+  if (n1 < 0) return false;
+  int n2 = 0;
+  if (tta) {
+    n2 = warp_compact(map2, bits2, thr2, ws, n1, lane);
+    if (n2 < 0) return false;
+  }
+  warp_finish_list<H, W, LOGITS>(p, ws, 0, n1, 0, mx1, lane);
   int n = n1;
   if (tta) {
-    if (lane == 0) bulk_load(ws.tile, p.maps_flip + (size_t)(b * K + kf) * NPX, NPX * 4, &ws.bar);
-    warp_finish_list<H, W>(p, ws, 0, n1, 0, mx1, lane);  // overlaps the flipped pass's copy
-    const int n2 = warp_compact<H, W>(p, ws, n1, lane, phase, mx2);
-    if (n2 < 0) { issue_next(); return false; }
-    warp_finish_list<H, W>(p, ws, n1, n2, 1, mx2, lane);
+    warp_finish_list<H, W, LOGITS>(p, ws, n1, n2, 1, mx2, lane);
     // merged = (P + mirror(Pf)) * 0.5, pixel by pixel in fp32 exactly like the reference: an entry of
     // the first list absorbs the matching entry of the second; unmatched entries are halved on their own
     for (int i = lane; i < n1; i += 32) {
@@ -520,39 +524,57 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
     }
     n = n1 + n2;
     __syncwarp();
-  } else {
-    warp_finish_list<H, W>(p, ws, 0, n1, 0, mx1, lane);
   }
 
-  // ---- bounding box and size of the support ----
-  int ymin = H, ymax = -1, xmin = W, xmax = -1, nnz = 0;
-  for (int i = lane; i < n; i += 32) {
-    if (ws.val[i] != 0.f) {
-      const int yx = ws.idx[i], y = yx >> 8, x = yx & 255;
+  // ---- keep the support only (non-zero entries), order preserved; bounding box ----
+  int nnz = 0;
+  int ymin = H, ymax = -1, xmin = W, xmax = -1;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const float v = i < n ? ws.val[i] : 0.f;
+    const int yx = i < n ? ws.idx[i] : 0;
+    const bool nz = v != 0.f;
+    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+    __syncwarp();  // the chunk is read before entries move down into it
+    if (nz) {
+      const int pos = nnz + __popc(bal & lt_mask);
+      ws.val[pos] = v;
+      ws.idx[pos] = (unsigned short)yx;
+      const int y = yx >> 8, x = yx & 255;
       ymin = min(ymin, y); ymax = max(ymax, y); xmin = min(xmin, x); xmax = max(xmax, x);
-      ++nnz;
     }
+    nnz += __popc(bal);
   }
+  __syncwarp();
   ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
   xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-  nnz = __reduce_add_sync(0xffffffffu, nnz);
-  const bool nonempty = ymax >= 0;
+  const bool nonempty = nnz > 0;
 
-  float4* gout = p.merged_out ? reinterpret_cast<float4*>(p.merged_out + (size_t)item * NPX) : nullptr;
-  if (gout) {
-#pragma unroll 4
-    for (int j = 0; j < NPX / 128; ++j) gout[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    for (int i = lane; i < n; i += 32)
-      if (ws.val[i] != 0.f) p.merged_out[(size_t)item * NPX + (ws.idx[i] >> 8) * W + (ws.idx[i] & 255)] = ws.val[i];
-  }
-
-  const int rad = p.radius[k];
-  const float* g = s_taps[k];  // shared-memory copy: the lookups below are lane-divergent
+  const float* gt = ws.taps + rad;
+  auto g = [&](int d) { return gt[min(d, rad + 1)]; };  // g(d), 0 for d > rad (the table is zero-padded)
   int best_i = 0;
   float conf = 0.f, lx = 0.f, ly = 0.f;
-  bool issued = false;
   if (nonempty) {
+    // C = sum_s w_s g(dy) g(dx) (+ the reflected images at -1 - s and 2H - 1 - s), evaluated directly
+    auto eval_c = [&](int qy, int qx) -> float {
+      float acc = 0.f;
+      for (int s = 0; s < nnz; ++s) {
+        const float w = ws.val[s];
+        const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
+        float fy = g(abs(qy - sy));
+        float fx = g(abs(qx - sx));
+        if (sy < rad || sy >= H - rad) {  // warp-uniform test
+          fy += g(qy + 1 + sy);
+          fy += g(2 * H - 1 - sy - qy);
+        }
+        if (sx < rad || sx >= W - rad) {
+          fx += g(qx + 1 + sx);
+          fx += g(2 * W - 1 - sx - qx);
+        }
+        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(w, fy), fx));
+      }
+      return acc;
+    };
     // The arg max of C lies inside the support's bounding box (the OKS kernel is non-negative and
     // decreasing in |d|), extended to the border where a reflected image can pull it outwards.
     const int sy0 = ymin <= rad - 1 ? 0 : ymin, sy1 = ymax >= H - rad ? H - 1 : ymax;
@@ -560,63 +582,24 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
     const int bw = sx1 - sx0 + 1, area = (sy1 - sy0 + 1) * bw;
     float best = -INFINITY;
     best_i = 0x7fffffff;
-    float cc, cl, cr, cu, cd;  // C at the peak and its 4 neighbours
-    if (area <= 192) {  // direct evaluation costs ~area * nnz; the tile path ~200 * nnz + a scan of the rows
-      // ---- compact support: evaluate C = sum_s w_s g(dy) g(dx) (+ reflections) directly at the
-      // pixels of the box; the tile is not needed, so the next map's copy starts now ----
-      issue_next();
-      issued = true;
-      auto eval_c = [&](int qy, int qx) -> float {
-        float acc = 0.f;
-        for (int s = 0; s < n; ++s) {
-          const float w = ws.val[s];
-          if (w == 0.f) continue;  // warp-uniform
-          const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
-          const int dy = abs(qy - sy), dx = abs(qx - sx);
-          float fy = dy <= rad ? g[rad + dy] : 0.f;
-          float fx = dx <= rad ? g[rad + dx] : 0.f;
-          if (sy < rad || sy >= H - rad) {  // images at -1 - sy and 2H - 1 - sy (warp-uniform test)
-            const int d1 = qy + 1 + sy, d2 = 2 * H - 1 - sy - qy;
-            if (d1 <= rad) fy += g[rad + d1];
-            if (d2 <= rad) fy += g[rad + d2];
-          }
-          if (sx < rad || sx >= W - rad) {
-            const int d1 = qx + 1 + sx, d2 = 2 * W - 1 - sx - qx;
-            if (d1 <= rad) fx += g[rad + d1];
-            if (d2 <= rad) fx += g[rad + d2];
-          }
-          acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(w, fy), fx));
-        }
-        return acc;
-      };
+    if (area <= kBoxPix) {
+      // ---- compact support: every pixel of the box ----
       for (int q0 = 0; q0 < area; q0 += 32) {
         const int q = min(q0 + lane, area - 1);  // the duplicate of the last pixel never wins a tie
         const int qy = sy0 + q / bw, qx = sx0 + q % bw;
         const float c = eval_c(qy, qx);
         if (c > best) { best = c; best_i = qy * W + qx; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-      }
-      if (!(best > 0.f)) best_i = 0;  // weights underflowed: C == 0 everywhere, first maximum is pixel 0
-      const int ys = best_i / W, xs = best_i % W;
-      // lanes 0..4: centre, left, right, up, down (clamped to the map; only used for interior peaks)
-      const int ddx = lane == 1 ? -1 : (lane == 2 ? 1 : 0), ddy = lane == 3 ? -1 : (lane == 4 ? 1 : 0);
-      const float v = eval_c(min(max(ys + ddy, 0), H - 1), min(max(xs + ddx, 0), W - 1));
-      cc = __shfl_sync(0xffffffffu, v, 0); cl = __shfl_sync(0xffffffffu, v, 1); cr = __shfl_sync(0xffffffffu, v, 2);
-      cu = __shfl_sync(0xffffffffu, v, 3); cd = __shfl_sync(0xffffffffu, v, 4);
     } else {
-      // ---- scattered support: every source adds w * g(dy) g(dx) (+ reflections) into the warp's tile ----
+      // ---- scattered support: every source adds w * g(dy) g(dx) (+ reflections) into the warp's 64 x 48
+      // tile; the arg max is searched over the rows of the box ----
+      // (measured: a pool of 3 tiles per 8 warps at twice the occupancy loses more to waiting than it gains)
       const int zy0 = max(0, ymin - rad - 1), zy1 = min(H - 1, ymax + rad + 1);
-      float4* t4 = reinterpret_cast<float4*>(ws.tile);
+      float4* t4 = reinterpret_cast<float4*>(tile);
       for (int i = zy0 * (W / 4) + lane; i < (zy1 + 1) * (W / 4); i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
-      for (int s = 0; s < n; ++s) {
+      for (int s = 0; s < nnz; ++s) {
         const float w = ws.val[s];
-        if (w == 0.f) continue;  // warp-uniform
         const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
         const int y0 = max(0, sy - rad), y1 = min(H - 1, sy + rad), x0 = max(0, sx - rad), x1 = min(W - 1, sx + rad);
         // 1-D factors over the window: the direct tap plus the taps of the two reflected images;
@@ -624,23 +607,12 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
         float fx = 0.f;
         if (lane <= 2 * rad) {
           const int yy = y0 + lane, xx = x0 + lane;
-          if (yy <= y1) {
-            float f = g[rad + abs(yy - sy)];
-            const int d1 = yy + 1 + sy, d2 = 2 * H - 1 - sy - yy;
-            if (d1 <= rad) f += g[rad + d1];
-            if (d2 <= rad) f += g[rad + d2];
-            ws.fac[lane] = __fmul_rn(w, f);
-          }
-          if (xx <= x1) {
-            fx = g[rad + abs(xx - sx)];
-            const int d1 = xx + 1 + sx, d2 = 2 * W - 1 - sx - xx;
-            if (d1 <= rad) fx += g[rad + d1];
-            if (d2 <= rad) fx += g[rad + d2];
-          }
+          if (yy <= y1) ws.fac[lane] = __fmul_rn(w, g(abs(yy - sy)) + g(yy + 1 + sy) + g(2 * H - 1 - sy - yy));
+          if (xx <= x1) fx = g(abs(xx - sx)) + g(xx + 1 + sx) + g(2 * W - 1 - sx - xx);
         }
         __syncwarp();
         if (x0 + lane <= x1) {  // lane = window column; the window rows are independent read-modify-writes
-          float* c = ws.tile + y0 * W + x0 + lane;
+          float* c = tile + y0 * W + x0 + lane;
           const int rows = y1 - y0 + 1;
           float cv[kTaps];
 #pragma unroll
@@ -660,30 +632,40 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
         if (c.z > best) { best = c.z; best_i = 4 * i + 2; }
         if (c.w > best) { best = c.w; best_i = 4 * i + 3; }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-      }
-      if (!(best > 0.f)) best_i = 0;
-      const float* c = ws.tile + best_i;
-      const int ys = best_i / W;
-      const bool in = ys >= 1 && ys < H - 1 && ys - 1 >= zy0 && ys + 1 <= zy1 && best_i % W >= 1 && best_i % W < W - 1;
-      cc = in ? c[0] : 0.f; cl = in ? c[-1] : 0.f; cr = in ? c[1] : 0.f; cu = in ? c[-W] : 0.f; cd = in ? c[W] : 0.f;
-      __syncwarp();  // the tile is read above and refilled by the next copy
     }
-    const int ys = best_i / W, xs = best_i % W;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (!(best > 0.f)) best_i = 0;  // weights underflowed: C == 0 everywhere, first maximum is pixel 0
+      const int ys = best_i / W, xs = best_i % W;
     lx = (float)xs; ly = (float)ys;
-    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) subpixel(cc, cl, cr, cu, cd, lx, ly);
-    // conf = merged heatmap at the integer peak (at most one non-zero entry per pixel after the merge)
+    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {
+      // lanes 0..4: centre, left, right, up, down
+      const int ddx = lane == 1 ? -1 : (lane == 2 ? 1 : 0), ddy = lane == 3 ? -1 : (lane == 4 ? 1 : 0);
+      const float v = eval_c(ys + ddy, xs + ddx);
+      const float cc = __shfl_sync(0xffffffffu, v, 0), cl = __shfl_sync(0xffffffffu, v, 1), cr = __shfl_sync(0xffffffffu, v, 2);
+      const float cu = __shfl_sync(0xffffffffu, v, 3), cd = __shfl_sync(0xffffffffu, v, 4);
+      subpixel(cc, cl, cr, cu, cd, lx, ly);
+    }
+    // conf = merged heatmap at the integer peak (one entry per pixel after the merge)
     const int pyx = (ys << 8) | xs;
     float cv = 0.f;
-    for (int i = lane; i < n; i += 32)
-      if (ws.idx[i] == pyx && ws.val[i] != 0.f) cv = ws.val[i];
+    for (int i = lane; i < nnz; i += 32)
+      if (ws.idx[i] == pyx) cv = ws.val[i];
     conf = warp_sum(cv);
   }
-  if (!issued) issue_next();
+
+  if (p.merged_out) {
+    float4* gout = reinterpret_cast<float4*>(p.merged_out + (size_t)item * NPX);
+#pragma unroll 4
+    for (int j = 0; j < NPX / 128; ++j) gout[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    for (int i = lane; i < nnz; i += 32)
+      p.merged_out[(size_t)item * NPX + (ws.idx[i] >> 8) * W + (ws.idx[i] & 255)] = ws.val[i];
+  }
   if (lane == 0) {
     float* rec = p.records + (size_t)item * PP_RECORD_FLOATS;
     rec[0] = lx;
@@ -691,95 +673,41 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
     rec[2] = conf;
   }
   if (lane >= 4 && lane < 8) write_scalars(p, b, k, kf, lane - 4);
-  __syncwarp();
   return true;
 }
 
 struct __align__(16) DecodeSmem {
-  WarpScratch warp[kDecWarps];
+  float planes[kDecWarps * 64 * 48];  // sparse path: one scatter tile per warp; dense path: P, row-convolved, C
+  WarpList warp[kDecWarps];
   float red_f[2][kDenseWarps][4];
   int red_i[2][kDenseWarps][4];
-  float taps[PP_MAX_KEYPOINTS][kTaps + 1];
-  int queue[kQueueCap];
+  int queue[kDecWarps];
   int q_count;
-  int next;   // next map of this CTA's range
-  int all_done;
 };
 
-template <int H, int W>
-__global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const __grid_constant__ DecodeParams p) {
+// One warp per map, kDecWarps consecutive maps per CTA, several CTAs per SM (the whole batch-256
+// workload is resident at once); maps the sparse path declines are decoded afterwards by the CTA.
+template <int H, int W, bool LOGITS>
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_kernel(const __grid_constant__ DecodeParams p) {
   constexpr int NPX = H * W;
-  static_assert(sizeof(WarpScratch) * kDecWarps >= 3 * NPX * sizeof(float), "dense planes alias the warp scratch");
+  static_assert(NPX == 64 * 48, "planes are sized for 64 x 48 maps");
   extern __shared__ __align__(16) uint8_t dec_smem_raw[];
   DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(dec_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // this CTA's contiguous range of maps (balanced to +-1)
-  const int per = p.count / gridDim.x, rem = p.count % gridDim.x;
-  const int first = blockIdx.x * per + min((int)blockIdx.x, rem);
-  const int cnt = per + ((int)blockIdx.x < rem ? 1 : 0);
   pdl_launch_dependents();
-  if (threadIdx.x == 0) { sm.q_count = 0; sm.next = 0; sm.all_done = 0; }
-  for (int i = threadIdx.x; i < PP_MAX_KEYPOINTS * (kTaps + 1); i += kDecThreads) (&sm.taps[0][0])[i] = (&p.taps[0][0])[i];
-  if (lane == 0) {
-    const uint32_t m = (uint32_t)__cvta_generic_to_shared(&sm.warp[warp].bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (threadIdx.x == 0) sm.q_count = 0;
   __syncthreads();
   pdl_wait();  // the logits / scalars come from the previous kernels of the stream
-  const bool tta = p.maps_flip != nullptr;
-  uint32_t phase = 0;
-
-  // next map of this CTA's range for this warp, or -1 (range exhausted / dense queue filling up);
-  // its flipped pass and a map one round ahead are pulled towards L2 meanwhile
-  auto fetch = [&]() -> int {
-    int it = -1;
-    if (lane == 0) {
-      if (*reinterpret_cast<volatile int*>(&sm.q_count) < kQueueThresh) {
-        it = atomicAdd(&sm.next, 1);
-        if (it >= cnt) it = -1;
-      }
-      if (it >= 0) {
-        const int K = p.num_kpts, item = first + it;
-        if (tta) bulk_prefetch_l2(p.maps_flip + (size_t)((item / K) * K + p.flip_idx[item % K]) * NPX, NPX * 4);
-        if (it + kDecWarps < cnt) bulk_prefetch_l2(p.maps + (size_t)(item + kDecWarps) * NPX, NPX * 4);
-      }
+  const int item = blockIdx.x * kDecWarps + warp;
+  if (item < p.count) {
+    if (!decode_sparse<H, W, LOGITS>(p, item, sm.warp[warp], lane, sm.planes + warp * NPX)) {
+      if (lane == 0) sm.queue[atomicAdd(&sm.q_count, 1)] = item;
     }
-    return __shfl_sync(0xffffffffu, it, 0);
-  };
-  WarpScratch& ws = sm.warp[warp];
-
-  while (true) {
-    // ---- sparse phase: warps pull maps until the range is exhausted or the dense queue fills ----
-    int cur = fetch();
-    if (cur >= 0 && lane == 0) bulk_load(ws.tile, p.maps + (size_t)(first + cur) * NPX, NPX * 4, &ws.bar);
-    while (cur >= 0) {
-      int nxt = -2;  // not fetched yet
-      auto issue_next = [&]() {
-        __syncwarp();
-        nxt = fetch();
-        if (nxt >= 0 && lane == 0) bulk_load(ws.tile, p.maps + (size_t)(first + nxt) * NPX, NPX * 4, &ws.bar);
-      };
-      if (!decode_sparse<H, W>(p, first + cur, ws, sm.taps, lane, phase, issue_next)) {
-        if (lane == 0) sm.queue[atomicAdd(&sm.q_count, 1)] = first + cur;
-      }
-      cur = nxt;
-    }
-    __syncthreads();
-    // ---- dense phase: the whole CTA works through the queue ----
-    const int nq = sm.q_count;
-    float* planes = reinterpret_cast<float*>(&sm.warp[0]);
-    if (warp < kDenseWarps)
-      for (int q = 0; q < nq; ++q)
-        decode_dense<H, W>(p, sm.queue[q], planes, planes + NPX, planes + 2 * NPX, sm.red_f, sm.red_i);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      sm.q_count = 0;
-      sm.all_done = sm.next >= cnt ? 1 : 0;
-    }
-    __syncthreads();
-    if (sm.all_done) break;
   }
+  __syncthreads();
+  const int nq = sm.q_count;
+  for (int q = 0; q < nq; ++q)
+    decode_dense<H, W>(p, sm.queue[q], sm.planes, sm.planes + NPX, sm.planes + 2 * NPX, sm.red_f, sm.red_i);
 }
 
 // 1-D factor of the reference's OKS kernel (post_processing.py:13-39), computed in double.
@@ -850,19 +778,16 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
   const int64_t count = (int64_t)batch * cfg->num_keypoints;
   PP_REQUIRE(count < (1ll << 31), PP_ERR_INVALID, "pp_decode: batch too large");
   p.count = (int)count;
-  static int sms = 0;
   static bool attr_set = false;
-  auto kern = decode_kernel<64, 48>;
-  if (!attr_set) {
-    int dev = 0;
-    PP_CHECK_CUDA(cudaGetDevice(&dev));
-    PP_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+  auto kern = cfg->input_is_logits ? decode_kernel<64, 48, true> : decode_kernel<64, 48, false>;
+  if (!attr_set) {  // shared memory for kDecCtasPerSm CTAs per SM (about 110 KB each)
+    PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  // one persistent CTA per SM; with few maps, enough CTAs that every warp has one
-  const int64_t want = (count + kDecWarps - 1) / kDecWarps;
-  const int grid = (int)(want < sms ? want : sms);
+  const int grid = (int)((count + kDecWarps - 1) / kDecWarps);
   PP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDecThreads), sizeof(DecodeSmem), (cudaStream_t)stream, p));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());

@@ -87,3 +87,25 @@ def make_crops(batch: int, seed: int = 0, height: int = 256, width: int = 192) -
     img = torch.nn.functional.interpolate(low, size=(height, width), mode="bilinear", align_corners=False)
     img = img * 200 + 55 * torch.rand(batch, 3, height, width, generator=g)
     return img.clamp(0, 255).to(torch.uint8)
+
+
+def planted_logit_pair(batch: int, seed: int = 0, device="cpu", keypoints: int = 17, height: int = 64, width: int = 48,
+                       flip_indices=(0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15)):
+    """Trained-model-like heatmap logits ("planted peaks"): per map
+    a * exp(-r^2 / 2 s^2) + N(0, 0.05), centre uniform over the map including the border, a in [2, 8],
+    s in [1, 3]; plus the matching flipped-pass logits (mirror image of the partner keypoint's map, amplitude
+    +-10 %, fresh noise), as flip-TTA sees them.  Returns (logits, logits_flipped_pass) on `device`."""
+    g = torch.Generator().manual_seed(seed)
+    cx = (torch.rand(batch, keypoints, 1, 1, generator=g) * width - 0.5).to(device)
+    cy = (torch.rand(batch, keypoints, 1, 1, generator=g) * height - 0.5).to(device)
+    a = (2 + 6 * torch.rand(batch, keypoints, 1, 1, generator=g)).to(device)
+    s = (1 + 2 * torch.rand(batch, keypoints, 1, 1, generator=g)).to(device)
+    scale = (0.9 + 0.2 * torch.rand(batch, keypoints, 1, 1, generator=g)).to(device)
+    yy = torch.arange(height, device=device, dtype=torch.float32).view(1, 1, height, 1)
+    xx = torch.arange(width, device=device, dtype=torch.float32).view(1, 1, 1, width)
+    bump = a * torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+    gd = torch.Generator(device=device).manual_seed(seed + 1) if str(device) != "cpu" else g
+    z = bump + 0.05 * torch.randn(bump.shape, generator=gd, device=device)
+    inv = torch.argsort(torch.tensor(flip_indices)).to(device)
+    zf = (bump * scale)[:, inv].flip(-1) + 0.05 * torch.randn(bump.shape, generator=gd, device=device)
+    return z.contiguous(), zf.contiguous()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch the fused decode kernel a few times on one input family (for ncu captures).
 
-    python tools/decode_probe.py planted|noise1|flat|planted_alt [batch] [tta] [iters]
+    python tools/decode_probe.py planted|noise1|flat|pair (+ _alt: alternate plain / TTA launches) [batch] [tta] [iters]
 """
 import os
 import sys
@@ -23,12 +23,17 @@ def main():
     iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     gen = {"planted": lambda s: cases.planted_peak_logits(batch, seed=s),
            "noise1": lambda s: cases.noise_logits(batch, s, 1.0),
-           "flat": lambda s: cases.noise_logits(batch, s, 1e-3)}[fam]
-    z = torch.from_numpy(gen(1)).cuda()
-    zf = torch.from_numpy(gen(2)).cuda() if tta else None
+           "flat": lambda s: cases.noise_logits(batch, s, 1e-3), "pair": None}[fam]
+    pair = fam == "pair"
+    if pair:
+        a, b = cases.planted_peak_pair(batch, 1)
+        z, zf2 = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    else:
+        z = torch.from_numpy(gen(1)).cuda()
+    zf = (zf2 if pair else torch.from_numpy(gen(2)).cuda()) if tta else None
     fi = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]
     if fam_alt:
-        zf = torch.from_numpy(gen(2)).cuda()
+        zf = zf2 if pair else torch.from_numpy(gen(2)).cuda()
         for _ in range(iters):  # alternate plain / TTA launches (tools/ncu_traffic.py expects this order)
             ops.decode(z, input_is_logits=True)
             ops.decode(z, zf, fi, input_is_logits=True)
