@@ -150,6 +150,22 @@ PP_API int pp_operand_from_f32(int32_t precision, const float* src, int64_t rows
                         void* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Global multi-head self-attention of one ViT layer on the tensor cores.  Replaces
+ * mmpretrain 1.2.0 MultiheadAttention.forward between its qkv and proj Linears:
+ *   q, k, v = qkv.reshape(B, N, 3, heads, d_h).permute(2, 0, 3, 1, 4)
+ *   x = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, heads * d_h)
+ * (external package, called from the config's backbone, see SURVEY.md 8c "Backbone").
+ *  qkv_op   operand (batch * tokens, 3 * heads * head_dim) in `precision` (the qkv GEMM's
+ *           PP_OUT_OPERAND output: [q | k | v] column blocks, heads contiguous inside each)
+ *  out_op   operand (batch * tokens, heads * head_dim) out = the proj GEMM's A operand
+ *  impl     0 = default (tcgen05: S and P.V on the 5th-gen tensor cores, P kept in TMEM),
+ *           1 = mma.sync kernel, 2 = tcgen05 kernel (tests compare the two)
+ * Built for tokens == 192 and head_dim 32 / 64; tensor-core precisions only.
+ * ---------------------------------------------------------------------------------- */
+PP_API int pp_attention(int32_t precision, const void* qkv_op, int32_t batch, int32_t tokens, int32_t heads,
+                        int32_t head_dim, void* out_op, int32_t impl, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Crop front-end: one frame + per-person forward affine matrices -> the uint8
  * model inputs.  Replaces, per person on the host in the reference, TopdownAffine's
  *   cv2.warpAffine(img, warp_mat, (w, h), flags=cv2.INTER_LINEAR)

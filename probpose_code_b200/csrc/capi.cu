@@ -1,5 +1,5 @@
 // C-ABI glue: error string, version, launch counter.
-#include "common.cuh"
+#include "engine_ops.cuh"
 
 #include <string.h>
 
@@ -10,6 +10,11 @@ thread_local int64_t g_launch_count = 0;
 
 bool pdl_enabled() {
   static const bool on = getenv("PP_NO_PDL") == nullptr;
+  return on;
+}
+
+bool attention_use_tc() {
+  static const bool on = !(getenv("PP_ATTENTION") && strcmp(getenv("PP_ATTENTION"), "mma") == 0);
   return on;
 }
 
@@ -24,3 +29,16 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* pp_last_error(void) { return pp::g_error; }
 extern "C" const char* pp_version(void) { return "probpose_b200 0.1.0 sm_100a"; }
+
+extern "C" int pp_attention(int32_t precision, const void* qkv_op, int32_t batch, int32_t tokens, int32_t heads,
+                            int32_t head_dim, void* out_op, int32_t impl, void* stream) {
+  using namespace pp;
+  PP_REQUIRE(batch >= 0 && heads >= 1, PP_ERR_INVALID, "pp_attention: bad batch %d / heads %d", batch, heads);
+  PP_REQUIRE(batch == 0 || (qkv_op && out_op), PP_ERR_INVALID, "pp_attention: qkv_op and out_op must be non-NULL");
+  PP_REQUIRE(precision == PP_PREC_FP16X3 || precision == PP_PREC_BF16 || precision == PP_PREC_FP16, PP_ERR_UNSUPPORTED,
+             "pp_attention: precision %d is not a tensor-core mode", precision);
+  PP_REQUIRE(impl >= 0 && impl <= 2, PP_ERR_INVALID, "pp_attention: impl %d (0 default, 1 mma.sync, 2 tcgen05)", impl);
+  const bool tc = impl == 2 || (impl == 0 && attention_use_tc());
+  return tc ? launch_attention_tc(precision, qkv_op, batch, tokens, heads, head_dim, out_op, (cudaStream_t)stream)
+            : launch_attention_mma(precision, qkv_op, batch, tokens, heads, head_dim, out_op, (cudaStream_t)stream);
+}

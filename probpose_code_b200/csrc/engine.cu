@@ -315,7 +315,7 @@ static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int ba
     if (tc_attn) { g.out_kind = PP_OUT_OPERAND; g.ldd = 3 * D; }
     PP_TRY(gemm(e, g, st));
     PP_TRY(timed(e, PP_KC_ATTENTION, st, [&] {
-      return tc_attn ? launch_attention_mma(prec, e->at<>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st)
+      return tc_attn ? (attention_use_tc() ? launch_attention_tc : launch_attention_mma)(prec, e->at<>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st)
                      : launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st);
     }));
     g = gemm_args(e, M, D, D, e->at<>(e->a_op), e->at<>(L.wproj));

@@ -31,6 +31,9 @@ int launch_attention(int prec, const float* qkv, int batch, int n, int heads, in
 // (B * n, 3 * heads * dh) in `prec`; out_op the proj GEMM's A operand.
 bool attention_mma_supported(int n, int dh);
 int launch_attention_mma(int prec, const void* qkv_op, int batch, int n, int heads, int dh, void* out_op, cudaStream_t st);
+// Same contract on the tcgen05 pipe (attention_tc.cu): S and P.V as tcgen05.mma, P kept in TMEM.
+int launch_attention_tc(int prec, const void* qkv_op, int batch, int n, int heads, int dh, void* out_op, cudaStream_t st);
+bool attention_use_tc();  // capi.cu: true unless PP_ATTENTION=mma is set in the environment
 
 // fp32 token rows (B * hw, c) <-> fp32 NCHW (B, c, hw); NCHW -> operand rows.
 int launch_rows_to_nchw(const float* rows, int batch, int hw, int c, float* nchw, cudaStream_t st);

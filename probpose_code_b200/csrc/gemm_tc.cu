@@ -518,8 +518,8 @@ static EncodeTiledFn get_encode_fn() {
 
 // K-major 16-bit operand (rows x row_elems), box = box_cols (64 / 32) elements x box_rows,
 // 128- / 64-byte swizzle, OOB -> 0.
-static int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t row_elems, int box_rows, int box_cols,
-                            bool bf16) {
+int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t row_elems, int box_rows, int box_cols,
+                     bool bf16) {
   typedef std::tuple<const void*, int64_t, int64_t, int, int, bool> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;

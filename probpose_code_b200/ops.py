@@ -123,6 +123,32 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
     return out
 
 
+def attention(qkv_op: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int, precision: int, impl: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``pp_attention``: softmax(Q K^T d_h^-0.5) V per (image, head) on the tensor cores.  ``qkv_op`` is the operand
+    buffer (batch * tokens, 3 * heads * head_dim) of the qkv GEMM; returns the operand buffer (batch * tokens, heads * head_dim).
+    ``impl``: 0 default, 1 mma.sync kernel, 2 tcgen05 kernel."""
+    _need_cuda(qkv_op, "qkv_op", torch.uint8)
+    if out is None:
+        out = torch.zeros(lib().pp_operand_bytes(precision, batch * tokens, heads * head_dim), dtype=torch.uint8, device=qkv_op.device)
+    with torch.cuda.device(qkv_op.device):
+        check(lib().pp_attention(precision, qkv_op.data_ptr(), batch, tokens, heads, head_dim, out.data_ptr(), impl, _stream()),
+              "pp_attention")
+    return out
+
+
+def from_operand(buf: torch.Tensor, rows: int, k: int, precision: int) -> torch.Tensor:
+    """Operand buffer -> fp32 (rows, k) (tests / debugging; the inverse of :func:`to_operand`)."""
+    if precision == _lib.PREC_FP16X3:
+        h = buf.view(torch.float16).view(rows, 2 * k).float()
+        return (h[:, :k] + h[:, k:]) / 64.0
+    if precision == _lib.PREC_BF16:
+        return buf.view(torch.bfloat16).view(rows, k).float()
+    if precision == _lib.PREC_FP16:
+        return buf.view(torch.float16).view(rows, k).float()
+    return buf.view(torch.float32).view(rows, k).clone()
+
+
 def crop_warp(frame: torch.Tensor, warp_mats: torch.Tensor, out_hw=(256, 192), out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``pp_crop_warp``: frame uint8 BGR (H, W, 3) CUDA + forward affine matrices fp32 (N, 2, 3) CUDA ->
     crops uint8 BGR (N, 3, h, w), bit-identical to ``cv2.warpAffine(..., flags=cv2.INTER_LINEAR)`` per person
