@@ -3,13 +3,14 @@
 // Reference semantics: mmpretrain 1.2.0 MultiheadAttention.forward (see attention.cu) =
 //   softmax(Q K^T * d_h^-0.5) V per (image, head), Q / K / V = column blocks of the qkv GEMM output.
 //
-// One CTA (4 warps, one thread per query row) per (image, head), two CTAs per SM:
+// One CTA (8 warps) per (image, head), two CTAs per SM; a query row = a TMEM lane is shared by two threads
+// (warps w and w + 4 may access the same lane quarter) that split its 192 keys in halves:
 //   * TMA (cp.async.bulk.tensor, 64- / 128-byte swizzle) stages Q (two 128-row tiles: rows 0-127 and
 //     128-255, of which 128-191 are this image's), K and V straight out of the qkv operand,
 //   * S = Q K^T: tcgen05.mma M = 128, N = 192, K = d_h, fp32 accumulator in TMEM (192 columns),
-//   * softmax: every thread owns one TMEM lane = one query row: tcgen05.ld 32 columns at a time,
-//     row max, exp2, row sum; P goes back INTO THE SAME TMEM COLUMNS as packed 16-bit pairs
-//     (tcgen05.st) - per 32-key chunk [hi : 16 columns | lo : 16 columns] - no shared-memory round trip,
+//   * softmax: tcgen05.ld 32 columns at a time, row max (halves combined through shared memory), exp2,
+//     row sum; P goes back INTO THE SAME TMEM COLUMNS as packed 16-bit pairs
+//     (tcgen05.st) - per 32-key chunk [hi : 16 columns | lo : 16 columns] in that chunk's own columns - no shared-memory round trip,
 //   * O = P V: tcgen05.mma with the A operand read from TMEM and V consumed as stored (keys x d_h,
 //     i.e. an MN-major B operand), 12 k-steps of 16 keys into a d_h-column TMEM accumulator,
 //   * O / rowsum leaves as the proj GEMM's A operand.
@@ -31,7 +32,7 @@ int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t r
 
 namespace {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;
 constexpr int kNTok = 192;
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -48,6 +49,30 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Barrier wait of the 256 softmax threads: back off between polls so that the waiting CTA does not take
+// issue slots from the CTA that shares the SM (bounded like ptx::mbar_wait: a lost arrival traps).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 22)) __trap();
+  }
 }
 
 template <int N>
@@ -102,8 +127,10 @@ struct AttCfg {
   static constexpr int OFF_K = 2 * NOPS * Q_BYTES;
   static constexpr int OFF_V = OFF_K + NOPS * KV_BYTES;
   static constexpr int OFF_BAR = OFF_V + NOPS * KV_BYTES;
-  static constexpr int LOAD_BYTES = OFF_BAR;        // everything the TMA brings in
-  static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;  // barriers, tmem pointer, alignment slack
+  static constexpr int LOAD0_BYTES = NOPS * (Q_BYTES + KV_BYTES);  // Q tile 0 + K: what the first S needs
+  static constexpr int LOAD1_BYTES = NOPS * (Q_BYTES + KV_BYTES);  // Q tile 1 + V
+  static constexpr int OFF_X = OFF_BAR + 64;        // row max / row sum halves: float [2][2][128]
+  static constexpr int SMEM_BYTES = OFF_X + 2 * 2 * 128 * 4 + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 256;             // S / P: 192 columns, O: DH columns at 192
   static_assert(DH == 32 || DH == 64, "head width");
   static_assert(192 + DH <= TMEM_COLS, "accumulators exceed the allocation");
@@ -118,9 +145,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   extern __shared__ uint8_t att_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* s_bar = full_bar + 1;
-  uint64_t* o_bar = full_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 3);
+  uint64_t* full_bar1 = full_bar + 1;
+  uint64_t* s_bar = full_bar + 2;
+  uint64_t* o_bar = full_bar + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 4);
+  float* x_max = reinterpret_cast<float*>(smem + Cfg::OFF_X);  // [half][row]
+  float* x_sum = x_max + 2 * 128;
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,6 +161,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::prefetch_tensormap(&tm_q);
     ptx::prefetch_tensormap(&tm_kv);
     ptx::mbar_init(full_bar, 1);
+    ptx::mbar_init(full_bar1, 1);
     ptx::mbar_init(s_bar, 1);
     ptx::mbar_init(o_bar, 1);
     ptx::fence_barrier_init();
@@ -150,15 +181,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   auto sV = [&](int part) { return smem + Cfg::OFF_V + part * Cfg::KV_BYTES; };
 
   if (threadIdx.x == 0) {
-    ptx::mbar_arrive_expect_tx(full_bar, Cfg::LOAD_BYTES);
+    ptx::mbar_arrive_expect_tx(full_bar, Cfg::LOAD0_BYTES);
+    ptx::mbar_arrive_expect_tx(full_bar1, Cfg::LOAD1_BYTES);
     const int row0 = b * kNTok;
 #pragma unroll
     for (int part = 0; part < NOPS; ++part) {
       const int c = part * 3 * D + h * DH;  // q | k | v column blocks, lo plane 3 D further
       ptx::tma_load_2d(sQ(0, part), &tm_q, full_bar, c, row0);
       ptx::tma_load_2d(sK(part), &tm_kv, full_bar, c + D, row0);
-      ptx::tma_load_2d(sQ(1, part), &tm_q, full_bar, c, row0 + 128);  // rows 192.. belong to the next image (or are zero-filled): never stored
-      ptx::tma_load_2d(sV(part), &tm_kv, full_bar, c + 2 * D, row0);
+    }
+#pragma unroll
+    for (int part = 0; part < NOPS; ++part) {
+      const int c = part * 3 * D + h * DH;
+      ptx::tma_load_2d(sV(part), &tm_kv, full_bar1, c + 2 * D, row0);
+      ptx::tma_load_2d(sQ(1, part), &tm_q, full_bar1, c, row0 + 128);  // rows 192.. belong to the next image (or are zero-filled): never stored
     }
   }
 
@@ -182,11 +218,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::umma_commit(s_bar);
   };
   auto issue_o = [&]() {  // thread 0: O = P V, P read from TMEM
+    ptx::mbar_wait(full_bar1, 0);  // V (and Q tile 1) have landed
     ptx::tcgen05_fence_after();
     const uint32_t vh = ptx::kmajor_desc_lo(ptx::smem_u32(sV(0)));
     const uint32_t vl = vh + (Cfg::KV_BYTES >> 4);
     constexpr uint32_t KSTEP = (16 * ROWB) >> 4;  // 16 keys further
-    constexpr int PCH = SPLIT == 3 ? 32 : 16;     // TMEM columns per 32-key chunk of P
+    constexpr int PCH = 32;                       // TMEM columns per 32-key chunk of P (its own S columns)
 #pragma unroll
     for (int j = 0; j < kNTok / 16; ++j) {
       const uint32_t a_hi = t_s + PCH * (j >> 1) + 8 * (j & 1);
@@ -208,77 +245,91 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   // exp2 argument scale: d_h^-0.5 * log2(e); FP16X3 scores carry the operand scale 64 * 64
   const float c_exp = rsqrtf((float)DH) * 1.4426950408889634f * (SPLIT == 3 ? kAccScaleInv : 1.0f);
   const float p_exp = SPLIT == 3 ? 6.0f : 0.0f;  // P leaves the exponential already in operand units (x 2^6)
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const int q = warp & 3, hf = warp >> 2;  // TMEM lane quarter, and which half of the keys / of the O columns
+  const int row = q * 32 + lane;           // query row of the tile = TMEM lane
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  constexpr int CHH = kNTok / 64;          // 32-key chunks per half
+  constexpr int PCH = 32;  // P of a 32-key chunk overwrites that chunk's own S columns (no thread reads another's)
 
 #pragma unroll 1
   for (int tile = 0; tile < 2; ++tile) {
-    const bool active = tile == 0 || warp < 2;  // tile 1: only rows 128..191 are real
-    ptx::mbar_wait(s_bar, tile);
+    const bool active = tile == 0 || q < 2;  // tile 1: only rows 128..191 are real
+    mbar_wait_relaxed(s_bar, tile);
     ptx::tcgen05_fence_after();
-    float l = 1.f;
+    float mx = -INFINITY;
     if (active) {
-      float mx = -INFINITY;
 #pragma unroll 1
-      for (int ch = 0; ch < kNTok / 32; ++ch) {
+      for (int ch = hf * CHH; ch < (hf + 1) * CHH; ++ch) {
         float v[32];
         ptx::tmem_ld_32x32b_x32(t_s + lane_base + 32 * ch, v);
+        float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(v[i], v[i + 1]));
+        for (int i = 0; i < 32; i += 8) {
+          m4[0] = fmaxf(m4[0], fmaxf(v[i], v[i + 1])); m4[1] = fmaxf(m4[1], fmaxf(v[i + 2], v[i + 3]));
+          m4[2] = fmaxf(m4[2], fmaxf(v[i + 4], v[i + 5])); m4[3] = fmaxf(m4[3], fmaxf(v[i + 6], v[i + 7]));
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
-      l = 0.f;
+      x_max[hf * 128 + row] = mx;
+    }
+    __syncthreads();
+    if (active) {
+      mx = fmaxf(mx, x_max[(hf ^ 1) * 128 + row]);
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains (fixed order: deterministic)
 #pragma unroll 1
-      for (int ch = 0; ch < kNTok / 32; ++ch) {
+      for (int ch = hf * CHH; ch < (hf + 1) * CHH; ++ch) {
         float v[32];
         ptx::tmem_ld_32x32b_x32(t_s + lane_base + 32 * ch, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           v[i] = ex2f(fmaf(v[i] - mx, c_exp, p_exp));  // (s - max) first: exact for scores near the maximum
-          l += v[i];
+          l4[i & 3] += v[i];
         }
         if constexpr (SPLIT == 3) {
           uint32_t r[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) split_pair(v[2 * i], v[2 * i + 1], r[i], r[16 + i]);
-          tmem_st<32>(t_s + lane_base + 32 * ch, r);
+          tmem_st<32>(t_s + lane_base + PCH * ch, r);
         } else {
           uint32_t r[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] = pack_pair<BF16>(v[2 * i], v[2 * i + 1]);
-          tmem_st<16>(t_s + lane_base + 16 * ch, r);
+          tmem_st<16>(t_s + lane_base + PCH * ch, r);
         }
       }
+      x_sum[hf * 128 + row] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tmem_st_wait();
     }
     ptx::tcgen05_fence_before();
-    __syncthreads();  // P of all rows is in TMEM
+    __syncthreads();  // P of all rows is in TMEM, the row-sum halves in shared memory
     if (threadIdx.x == 0) issue_o();
-    ptx::mbar_wait(o_bar, tile);
+    mbar_wait_relaxed(o_bar, tile);
     ptx::tcgen05_fence_after();
     if (threadIdx.x == 0 && tile == 0) issue_s(1);  // overlaps the read-out of O below (disjoint columns)
     if (active) {
       // FP16X3: O carries 64 (P) * 64 (V) and the row sum carries 64, so O / l is already in operand units
-      const float inv = 1.0f / l;
-      const size_t orow = (size_t)b * kNTok + tile * 128 + threadIdx.x;
-      uint16_t* d = out_op + orow * (NOPS * D) + h * DH;
+      const float inv = 1.0f / (x_sum[row] + x_sum[128 + row]);
+      const size_t orow = (size_t)b * kNTok + tile * 128 + row;
+      uint16_t* d = out_op + orow * (NOPS * D) + h * DH + hf * (DH / 2);  // this thread's half of the head's columns
 #pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 32) {
-        float o[32];
-        ptx::tmem_ld_32x32b_x32(t_o + lane_base + c0, o);
-        uint32_t hi[16], lo[16];
+      for (int c0 = 0; c0 < DH / 2; c0 += 16) {
+        float o[16];
+        tmem_ld_x16(t_o + lane_base + hf * (DH / 2) + c0, o);
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           if constexpr (SPLIT == 3) split_pair(o[2 * i] * inv, o[2 * i + 1] * inv, hi[i], lo[i]);
           else hi[i] = pack_pair<BF16>(o[2 * i] * inv, o[2 * i + 1] * inv);
         }
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
+        for (int i = 0; i < 8; i += 4) {
           *reinterpret_cast<uint4*>(d + c0 + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
           if constexpr (SPLIT == 3) *reinterpret_cast<uint4*>(d + D + c0 + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
         }
       }
     }
     ptx::tcgen05_fence_before();
-    __syncthreads();  // O has been read: the next tile's P V may overwrite it
+    __syncthreads();  // O has been read: the next tile's P V may overwrite it (and the exchange arrays are free)
   }
   if (warp == 1) {
     ptx::tcgen05_fence_after();

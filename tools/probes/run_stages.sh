@@ -1,9 +1,6 @@
-for lib in libprobpose_b200.so libpp_var_2_8.so libpp_var_3_5.so; do
-export PROBPOSE_B200_LIB=$PWD/probpose_code_b200/$lib
-for fam in pair_alt noise1_alt; do
-  for b in 256 64; do
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:decode_kernel --csv --log-file gpurun_out/st.csv python tools/decode_probe.py $fam $b 0 3 > /dev/null 2>&1
-  echo "$lib $fam $b: $(grep decode_kernel gpurun_out/st.csv | awk -F'","' '{printf "%s ", $NF}' | tr -d '"')"
-  done
-done
+timeout 200 python -m pytest tests/test_attention_gpu.py -x -q 2>&1 | tail -1
+for d in 0; do
+  PP_ATT_DBG=$d ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:attention_tc --csv --log-file gpurun_out/st.csv python tools/probes/att_probe.py > /dev/null 2>&1
+  echo "dbg $d: $(grep attention_tc gpurun_out/st.csv | grep duration | awk -F'","' '{printf "%s ", $NF}' | tr -d '"')"
+  echo "inst: $(grep attention_tc gpurun_out/st.csv | grep inst_exec | awk -F'","' '{printf "%s ", $NF}' | tr -d '"')"
 done
