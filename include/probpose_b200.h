@@ -150,6 +150,30 @@ PP_API int pp_operand_from_f32(int32_t precision, const float* src, int64_t rows
                         void* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused UDPHeatmap (DARK-UDP) decode - the codec of the ViTPose td-hm configs.
+ * Replaces, per person on the host in the reference:
+ *   flip-TTA merge        mmpose/models/heads/heatmap_heads/heatmap_head.py:245-256 + tta.py:35-39
+ *   BaseHead.decode loop  mmpose/models/heads/base_head.py:57-77 (D2H of the heatmaps)
+ *   UDPHeatmap.decode     mmpose/codecs/udp_heatmap.py:146-196 (heatmap_type "gaussian")
+ *   get_heatmap_maximum / gaussian_blur   mmpose/codecs/utils/post_processing.py:178-249
+ *   refine_keypoints_dark_udp             mmpose/codecs/utils/refinement.py:102-160
+ *  maps / maps_flip   device fp32 (B, K, H, W) heatmaps of the plain / flipped pass (maps_flip NULL: no TTA)
+ *  records            device fp32 (B, K, 3) out: x, y in heatmap pixels (float32 like the reference's keypoints
+ *                     before udp_heatmap.py:194-195), score = maximum of the merged map.  Maps whose maximum is
+ *                     <= 0 give (-1, -1) unrefined (the reference refines those with samples wrapped around from
+ *                     the neighbouring keypoint's map).
+ *  merged_out         optional device fp32 (B, K, H, W): the merged heatmaps (test_cfg output_heatmaps)
+ * ---------------------------------------------------------------------------------- */
+typedef struct pp_udp_cfg {
+  int32_t num_keypoints;    /* K <= PP_MAX_KEYPOINTS                                        */
+  int32_t height, width;    /* heatmap size, 64 x 48                                        */
+  int32_t blur_kernel_size; /* 11 (sigma 2) / 17 (sigma 3): udp_heatmap.py:88-90            */
+} pp_udp_cfg;
+
+PP_API int pp_decode_udp(const pp_udp_cfg* cfg, const float* maps, const float* maps_flip, const int32_t* flip_indices,
+                         int32_t batch, float* records, float* merged_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Global multi-head self-attention of one ViT layer on the tensor cores.  Replaces
  * mmpretrain 1.2.0 MultiheadAttention.forward between its qkv and proj Linears:
  *   q, k, v = qkv.reshape(B, N, 3, heads, d_h).permute(2, 0, 3, 1, 4)

@@ -22,7 +22,7 @@ EXPORTS = [
     "pp_last_error", "pp_version", "pp_decode", "pp_gemm", "pp_operand_bytes", "pp_operand_from_f32",
     "pp_engine_workspace_bytes", "pp_engine_create", "pp_engine_destroy", "pp_engine_load", "pp_engine_finalize",
     "pp_engine_backbone", "pp_engine_head", "pp_engine_infer", "pp_engine_last_launch_count",
-    "pp_engine_profile_begin", "pp_engine_profile_end", "pp_crop_warp", "pp_attention",
+    "pp_engine_profile_begin", "pp_engine_profile_end", "pp_crop_warp", "pp_attention", "pp_decode_udp",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "decode", "other")
 
@@ -31,6 +31,10 @@ class DecodeCfg(C.Structure):
     _fields_ = [("num_keypoints", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
                 ("input_is_logits", C.c_int32), ("temperature", C.c_float), ("normalize", C.c_float),
                 ("error_divisor", C.c_float)]
+
+
+class UdpCfg(C.Structure):
+    _fields_ = [("num_keypoints", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("blur_kernel_size", C.c_int32)]
 
 
 class GemmArgs(C.Structure):
@@ -81,6 +85,8 @@ def lib() -> C.CDLL:
     l.pp_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     l.pp_crop_warp.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                C.c_int32, C.c_void_p]
+    l.pp_decode_udp.argtypes = [C.POINTER(UdpCfg), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p]
     l.pp_attention.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                C.c_void_p]
     if True:

@@ -1,0 +1,236 @@
+// Fused UDPHeatmap (DARK-UDP) decode for sm_100a - the decode of the ViTPose td-hm configs.
+//
+//   merged = 0.5 * (H + mirror(Hf[flip_idx[k]]))                       (flip-TTA, heatmap_head.py:245-256, tta.py:35-39)
+//   (x, y) = first arg max of merged, score = max ; (-1, -1) if max <= 0  (post_processing.py:178-217)
+//   B = zero-padded separable Gaussian blur (OpenCV float taps), rescaled to the old maximum (post_processing.py:220-249)
+//   L = log(clip(B, 1e-3, 50)), edge-padded ; gradient / Hessian of L at the peak from 7 samples ;
+//   (x, y) -= pinv(Hessian + eps I) grad                                 (refinement.py:102-160)
+//   record = [x, y, score]   (heatmap pixels; the caller applies udp_heatmap.py:194-195 in double)
+//
+// One CTA (8 warps) per (person, keypoint) map: the map is read once from HBM with coalesced 128-bit loads into a
+// shared-memory plane (the flipped pass merged in place), block-wide first-max reduction, row pass and column pass of
+// the blur through two more planes, block max of the blurred map; one thread then does the 7-sample refinement (the
+// Hessian solve in double, exactly where numpy promotes to float64).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace pp {
+
+namespace {
+
+constexpr int kUdpThreads = 256;
+constexpr int kUdpWarps = kUdpThreads / 32;
+constexpr int kUdpMaxTaps = 31;
+
+struct UdpParams {
+  const float* maps;
+  const float* maps_flip;
+  float* records;
+  float* merged_out;
+  int num_kpts;
+  int ntaps;
+  int flip_idx[PP_MAX_KEYPOINTS];
+  float taps[kUdpMaxTaps];
+};
+
+template <int H, int W>
+__global__ void __launch_bounds__(kUdpThreads, 4) udp_decode_kernel(const __grid_constant__ UdpParams p) {
+  constexpr int NPX = H * W, NV4 = NPX / 4, V = NV4 / kUdpThreads;
+  static_assert(NV4 % kUdpThreads == 0 && W % 4 == 0, "map must split into whole float4 per thread");
+  __shared__ __align__(16) float sP[NPX];  // merged heatmap
+  __shared__ __align__(16) float sR[NPX];  // row pass
+  __shared__ __align__(16) float sC[NPX];  // blurred map
+  __shared__ float red_v[kUdpWarps];
+  __shared__ int red_i[kUdpWarps];
+  __shared__ float red_b[kUdpWarps];
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int item = blockIdx.x, K = p.num_kpts;
+  const int b = item / K, k = item % K;
+  const bool tta = p.maps_flip != nullptr;
+  pdl_wait();
+
+  {
+    const float4* s1 = reinterpret_cast<const float4*>(p.maps + (size_t)item * NPX);
+#pragma unroll
+    for (int j = 0; j < V; ++j) reinterpret_cast<float4*>(sP)[tid + j * kUdpThreads] = ld_stream_f4(s1 + tid + j * kUdpThreads);
+    if (tta) {
+      const float4* s2 = reinterpret_cast<const float4*>(p.maps_flip + (size_t)(b * K + p.flip_idx[k]) * NPX);
+      float4 z[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) z[j] = ld_stream_f4(s2 + tid + j * kUdpThreads);
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int v4 = tid + j * kUdpThreads, y = v4 / (W / 4), xq = v4 % (W / 4);
+        const int dst = y * (W / 4) + (W / 4 - 1 - xq);  // mirrored float4 slot, components reversed
+        float4 a = reinterpret_cast<float4*>(sP)[dst];
+        a.x = (a.x + z[j].w) * 0.5f; a.y = (a.y + z[j].z) * 0.5f; a.z = (a.z + z[j].y) * 0.5f; a.w = (a.w + z[j].x) * 0.5f;
+        reinterpret_cast<float4*>(sP)[dst] = a;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- first maximum of the merged map (smallest flat index among equal maxima) ----
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  float4* gout = p.merged_out ? reinterpret_cast<float4*>(p.merged_out + (size_t)item * NPX) : nullptr;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int v4 = tid + j * kUdpThreads;
+    const float4 a = reinterpret_cast<const float4*>(sP)[v4];
+    if (gout) gout[v4] = a;
+    const float e[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (e[c] > best) { best = e[c]; best_i = 4 * v4 + c; }  // ascending index per thread
+  }
+  // NaN-free inputs assumed (np.argmax would return the first NaN)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if (lane == 0) { red_v[warp] = best; red_i[warp] = best_i; }
+
+  // ---- row pass of the blur: zero outside the map ----
+  const int rad = p.ntaps >> 1;
+  for (int i = tid; i < NPX; i += kUdpThreads) {
+    const int y = i / W, x = i % W;
+    const float* row = sP + y * W;
+    float acc = 0.f;
+    for (int j = 0; j < p.ntaps; ++j) {
+      const int xx = x + j - rad;
+      if (xx >= 0 && xx < W) acc = fmaf(row[xx], p.taps[j], acc);
+    }
+    sR[i] = acc;
+  }
+  __syncthreads();
+  // ---- column pass, maximum of the blurred map ----
+  float bmax = -INFINITY;
+  for (int i = tid; i < NPX; i += kUdpThreads) {
+    const int y = i / W, x = i % W;
+    float acc = 0.f;
+    for (int j = 0; j < p.ntaps; ++j) {
+      const int yy = y + j - rad;
+      if (yy >= 0 && yy < H) acc = fmaf(sR[yy * W + x], p.taps[j], acc);
+    }
+    sC[i] = acc;
+    bmax = fmaxf(bmax, acc);
+  }
+  bmax = warp_max(bmax);
+  if (lane == 0) red_b[warp] = bmax;
+  __syncthreads();
+
+  if (tid == 0) {
+    for (int w = 0; w < kUdpWarps; ++w) {
+      if (red_v[w] > best || (red_v[w] == best && red_i[w] < best_i)) { best = red_v[w]; best_i = red_i[w]; }
+      bmax = fmaxf(bmax, red_b[w]);
+    }
+    float* rec = p.records + (size_t)item * 3;
+    rec[2] = best;
+    if (!(best > 0.f)) {
+      // No response: the reference marks the keypoint (-1, -1) and then "refines" it with samples that wrap around
+      // into the neighbouring keypoint's map (refinement.py:130-138 on index 0) - not reproduced.
+      rec[0] = -1.f;
+      rec[1] = -1.f;
+    } else {
+      const int py = best_i / W, px = best_i % W;
+      // heatmaps[k] *= origin_max / (max + 1e-12): a float64 scalar times the float32 map, rounded to float32
+      const double scale = (double)best / ((double)bmax + 1e-12);
+      auto L = [&](int y, int x) -> float {  // log of the clipped, rescaled blurred map, edge-padded
+        y = min(max(y, 0), H - 1);
+        x = min(max(x, 0), W - 1);
+        const float v = (float)((double)sC[y * W + x] * scale);
+        return logf(fminf(fmaxf(v, 1e-3f), 50.0f));
+      };
+      const float i_ = L(py, px), ix1 = L(py, px + 1), iy1 = L(py + 1, px), ix1y1 = L(py + 1, px + 1);
+      const float ix1_y1_ = L(py - 1, px - 1), ix1_ = L(py, px - 1), iy1_ = L(py - 1, px);
+      const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_)), dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
+      const float dxx = __fadd_rn(__fsub_rn(ix1, __fmul_rn(2.f, i_)), ix1_);
+      const float dyy = __fadd_rn(__fsub_rn(iy1, __fmul_rn(2.f, i_)), iy1_);
+      float t = __fsub_rn(ix1y1, ix1);
+      t = __fsub_rn(t, iy1); t = __fadd_rn(t, i_); t = __fadd_rn(t, i_); t = __fsub_rn(t, ix1_); t = __fsub_rn(t, iy1_);
+      t = __fadd_rn(t, ix1_y1_);
+      const float dxy = __fmul_rn(0.5f, t);
+      // float64 from here on, like numpy (the eps * eye(2) term is float64): pinv of a symmetric 2 x 2
+      const double eps = 1.1920928955078125e-07;
+      const double a = (double)dxx + eps, c = (double)dyy + eps, bq = (double)dxy;
+      const double half_tr = 0.5 * (a + c), rt = sqrt(0.25 * (a - c) * (a - c) + bq * bq);
+      const double l1 = half_tr + rt, l2 = half_tr - rt;
+      const double smax = fmax(fabs(l1), fabs(l2)), smin = fmin(fabs(l1), fabs(l2));
+      double ox, oy;
+      if (smax == 0.0) {
+        ox = oy = 0.0;  // pinv(0) = 0
+      } else if (smin > 1e-15 * smax) {
+        const double det = a * c - bq * bq;
+        ox = (c * (double)dx - bq * (double)dy) / det;
+        oy = (a * (double)dy - bq * (double)dx) / det;
+      } else {
+        // rank 1: only the dominant eigen-pair survives numpy's rcond cut-off
+        const double l = fabs(l1) >= fabs(l2) ? l1 : l2;
+        double vx = bq, vy = l - a;
+        if (fabs(vx) + fabs(vy) == 0.0) { vx = l - c; vy = bq; }
+        if (fabs(vx) + fabs(vy) == 0.0) { vx = fabs(a) >= fabs(c) ? 1.0 : 0.0; vy = 1.0 - vx; }
+        const double n2 = vx * vx + vy * vy, proj = (vx * (double)dx + vy * (double)dy) / (n2 * l);
+        ox = vx * proj;
+        oy = vy * proj;
+      }
+      rec[0] = (float)((double)(float)px - ox);
+      rec[1] = (float)((double)(float)py - oy);
+    }
+  }
+}
+
+void fill_gaussian_taps(UdpParams& p, int ksize) {  // OpenCV getGaussianKernel(ksize, sigma <= 0) for CV_32F
+  const double sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8;
+  double g[kUdpMaxTaps], sum = 0;
+  for (int i = 0; i < ksize; ++i) {
+    const double x = i - (ksize - 1) * 0.5;
+    g[i] = exp(-(x * x) / (2 * sigma * sigma));
+    sum += g[i];
+  }
+  for (int i = 0; i < kUdpMaxTaps; ++i) p.taps[i] = i < ksize ? (float)(g[i] / sum) : 0.f;
+  p.ntaps = ksize;
+}
+
+}  // namespace
+
+}  // namespace pp
+
+extern "C" int pp_decode_udp(const pp_udp_cfg* cfg, const float* maps, const float* maps_flip, const int32_t* flip_indices,
+                             int32_t batch, float* records, float* merged_out, void* stream) {
+  using namespace pp;
+  PP_REQUIRE(cfg != nullptr, PP_ERR_INVALID, "pp_decode_udp: cfg must be non-NULL");
+  PP_REQUIRE(batch >= 0, PP_ERR_INVALID, "pp_decode_udp: negative batch %d", batch);
+  PP_REQUIRE(batch == 0 || (maps && records), PP_ERR_INVALID, "pp_decode_udp: maps and records must be non-NULL");
+  PP_REQUIRE(cfg->num_keypoints >= 1 && cfg->num_keypoints <= PP_MAX_KEYPOINTS, PP_ERR_INVALID,
+             "pp_decode_udp: num_keypoints %d outside [1, %d]", cfg->num_keypoints, PP_MAX_KEYPOINTS);
+  PP_REQUIRE(cfg->height == 64 && cfg->width == 48, PP_ERR_UNSUPPORTED, "pp_decode_udp: heatmap %dx%d not built (only 64x48)",
+             cfg->height, cfg->width);
+  PP_REQUIRE(cfg->blur_kernel_size >= 3 && cfg->blur_kernel_size <= kUdpMaxTaps && (cfg->blur_kernel_size & 1) == 1, PP_ERR_INVALID,
+             "pp_decode_udp: blur_kernel_size %d must be odd and in [3, %d] (post_processing.py:237)", cfg->blur_kernel_size, kUdpMaxTaps);
+  PP_REQUIRE(!maps_flip || flip_indices, PP_ERR_INVALID, "pp_decode_udp: maps_flip given without flip_indices");
+  if (batch == 0) return PP_OK;
+  UdpParams p;
+  p.maps = maps; p.maps_flip = maps_flip; p.records = records; p.merged_out = merged_out;
+  p.num_kpts = cfg->num_keypoints;
+  for (int k = 0; k < PP_MAX_KEYPOINTS; ++k) {
+    int f = k;
+    if (maps_flip && k < cfg->num_keypoints) {
+      f = flip_indices[k];
+      PP_REQUIRE(f >= 0 && f < cfg->num_keypoints, PP_ERR_INVALID, "pp_decode_udp: flip_indices[%d]=%d out of range", k, f);
+    }
+    p.flip_idx[k] = f;
+  }
+  fill_gaussian_taps(p, cfg->blur_kernel_size);
+  const int64_t count = (int64_t)batch * cfg->num_keypoints;
+  PP_REQUIRE(count < (1ll << 31), PP_ERR_INVALID, "pp_decode_udp: batch too large");
+  PP_CHECK_CUDA(launch_pdl(udp_decode_kernel<64, 48>, dim3((unsigned)count), dim3(kUdpThreads), 0, (cudaStream_t)stream, p));
+  count_launch();
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}

@@ -72,6 +72,31 @@ def decode(maps: torch.Tensor, maps_flip: Optional[torch.Tensor] = None,
     return (rec, merged) if return_heatmaps else rec
 
 
+def decode_udp(maps: torch.Tensor, maps_flip: Optional[torch.Tensor] = None, flip_indices: Optional[Sequence[int]] = None, *,
+               blur_kernel_size: int = 11, return_heatmaps: bool = False, out: Optional[torch.Tensor] = None):
+    """``pp_decode_udp``: fused flip-TTA merge + UDPHeatmap (DARK-UDP) decode.  ``maps`` fp32 CUDA (B, K, 64, 48).
+    Returns records fp32 (B, K, 3) = x, y in heatmap pixels, score (and the merged heatmaps if asked)."""
+    _need_cuda(maps, "maps")
+    if maps.dim() != 4:
+        raise ValueError(f"maps must be (B, K, H, W), got {tuple(maps.shape)}")
+    b, k, h, w = maps.shape
+    fi = None
+    if maps_flip is not None:
+        _need_cuda(maps_flip, "maps_flip")
+        if maps_flip.shape != maps.shape:
+            raise ValueError("maps_flip must have the shape of maps")
+        if flip_indices is None or len(flip_indices) != k:
+            raise ValueError("flip_indices must list one partner per keypoint")  # heatmap_head.py:247, tta.py:37
+        fi = (C.c_int32 * k)(*[int(i) for i in flip_indices])
+    cfg = _lib.UdpCfg(k, h, w, int(blur_kernel_size))
+    rec = out if out is not None else torch.empty((b, k, 3), dtype=torch.float32, device=maps.device)
+    merged = torch.empty_like(maps) if return_heatmaps else None
+    with torch.cuda.device(maps.device):
+        check(lib().pp_decode_udp(C.byref(cfg), _ptr(maps), _ptr(maps_flip), fi, b, _ptr(rec), _ptr(merged), _stream()),
+              "pp_decode_udp")
+    return (rec, merged) if return_heatmaps else rec
+
+
 def to_operand(x: torch.Tensor, precision: int) -> torch.Tensor:
     """fp32 (rows, k) CUDA -> GEMM operand buffer (uint8 tensor) in ``precision``."""
     _need_cuda(x, "x")
