@@ -223,7 +223,15 @@ typedef struct pp_engine_cfg {
   float bn_eps;             /* 1e-5                                                        */
   float temperature, normalize; /* 0.5, 1.0                                                */
   float mean[3], std[3];    /* RGB order, applied after BGR->RGB                           */
+  int32_t head_kind;        /* PP_HEAD_PROBMAP (ProbMapHead + ProbMap codec) or PP_HEAD_HEATMAP
+                               (HeatmapHead + UDPHeatmap codec: the ViTPose td-hm configs,
+                               heads/heatmap_heads/heatmap_head.py:197-268; pp_engine_head then
+                               returns the heatmaps and ignores `scalars`, pp_engine_infer writes
+                               (B, K, 3) records = x, y, score as pp_decode_udp does)          */
+  int32_t blur_kernel_size; /* PP_HEAD_HEATMAP: UDPHeatmap blur kernel (11)                  */
 } pp_engine_cfg;
+
+enum { PP_HEAD_PROBMAP = 0, PP_HEAD_HEATMAP = 1 };
 
 typedef struct pp_engine pp_engine;
 

@@ -201,3 +201,41 @@ class ProbPoseRef(nn.Module):
         rec[..., 5] = oks.numpy()
         rec[..., 6] = err.numpy() / math.sqrt(h**2 + w**2)  # probmap_head.py:786-787
         return rec
+
+
+class ViTPoseRef(nn.Module):
+    """TopdownPoseEstimator(backbone=ViT, head=HeatmapHead, codec=UDPHeatmap) restricted to ``predict``
+    (configs/body_2d_keypoint/topdown_heatmap/coco/td-hm_ViTPose-*_coco-256x192.py; heatmap_head.py:197-268).
+    The head's deconv stack and final layer are the same modules as ProbMapHead's heatmap branch."""
+
+    def __init__(self, **vit_kwargs):
+        super().__init__()
+        self.backbone = VisionTransformerRef(**vit_kwargs)
+        self.head = ProbMapHeadRef(in_channels=self.backbone.ln1.normalized_shape[0])
+
+    preprocess = staticmethod(ProbPoseRef.preprocess)
+
+    def load_state_dict(self, sd, strict=True):  # HeatmapHead checkpoints carry no scalar branches
+        own = self.state_dict()
+        own.update({k: v for k, v in sd.items() if k in own})
+        return super().load_state_dict(own, strict=strict)
+
+    @torch.no_grad()
+    def heatmaps(self, inputs, flip_test=True, flip_indices=decode_oracle.COCO_FLIP_INDICES):
+        hm = self.head.heatmap_logits(self.backbone(inputs)[-1])
+        if flip_test:  # heatmap_head.py:245-256, tta.py:35-39
+            hmf = self.head.heatmap_logits(self.backbone(inputs.flip(-1))[-1])
+            hm = (hm + hmf.flip(-1)[:, flip_indices]) * 0.5
+        return hm
+
+    @torch.no_grad()
+    def predict(self, inputs, flip_test=True):
+        """Records (B, K, 3) float64: x, y in input pixels, score - through the restated reference decode."""
+        from . import udp_oracle
+
+        hm = self.heatmaps(inputs, flip_test).numpy()
+        kpts, scores = udp_oracle.decode_instances(hm)
+        rec = np.zeros((hm.shape[0], hm.shape[1], 3))
+        rec[..., :2] = np.concatenate(kpts, 0)
+        rec[..., 2] = np.concatenate(scores, 0)
+        return rec

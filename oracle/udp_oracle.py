@@ -88,6 +88,29 @@ def refine_dark_udp(keypoints: np.ndarray, heatmaps: np.ndarray, blur_kernel_siz
     return keypoints
 
 
+def hessian_min_eig(heatmaps: np.ndarray, blur_kernel_size: int = 11) -> np.ndarray:
+    """Per map, the smallest |eigenvalue| of the DARK-UDP Hessian at the peak (a trained sigma = 2 Gaussian gives
+    ~1/8 after the blur).  Where it is tiny (flat or clipped maps) the refinement step amplifies the float rounding of
+    the blur without bound - tests use this to say where a pixel tolerance is meaningful."""
+    hm = heatmaps.copy()
+    locs, _ = heatmap_maximum(hm)
+    hm = gaussian_blur(hm, blur_kernel_size)
+    np.clip(hm, 1e-3, 50.0, hm)
+    np.log(hm, hm)
+    pad = np.pad(hm, ((0, 0), (1, 1), (1, 1)), mode="edge")
+    out = np.zeros(len(hm))
+    for k, (x, y) in enumerate(locs.astype(int)):
+        if x < 0:
+            continue
+        p = pad[k].astype(np.float64)
+        x, y = x + 1, y + 1
+        dxx = p[y, x + 1] - 2 * p[y, x] + p[y, x - 1]
+        dyy = p[y + 1, x] - 2 * p[y, x] + p[y - 1, x]
+        dxy = 0.5 * (p[y + 1, x + 1] - p[y, x + 1] - p[y + 1, x] + 2 * p[y, x] - p[y, x - 1] - p[y - 1, x] + p[y - 1, x - 1])
+        out[k] = np.abs(np.linalg.eigvalsh(np.array([[dxx, dxy], [dxy, dyy]]))).min()
+    return out
+
+
 def udp_decode(heatmaps: np.ndarray, input_size=(192, 256), blur_kernel_size: int = 11):
     """UDPHeatmap.decode (udp_heatmap.py:146-196, gaussian): (K, H, W) float32 -> keypoints (1, K, 2) float64 in
     input-image pixels, scores (1, K) float32."""

@@ -15,6 +15,7 @@ PRECISIONS = {"fp16x3": PREC_FP16X3, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp32
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 OUT_F32, OUT_OPERAND, OUT_PLANES = 0, 1, 2
 RECORD_FLOATS = 7
+HEAD_PROBMAP, HEAD_HEATMAP = 0, 1
 MAX_KEYPOINTS = 17
 
 # every symbol include/probpose_b200.h declares (tests check they are all exported)
@@ -52,7 +53,8 @@ class EngineCfg(C.Structure):
                 ("patch", C.c_int32), ("patch_pad", C.c_int32), ("embed_dim", C.c_int32), ("depth", C.c_int32),
                 ("heads", C.c_int32), ("ffn_dim", C.c_int32), ("num_keypoints", C.c_int32),
                 ("deconv_channels", C.c_int32), ("ln_eps", C.c_float), ("bn_eps", C.c_float),
-                ("temperature", C.c_float), ("normalize", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+                ("temperature", C.c_float), ("normalize", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3),
+                ("head_kind", C.c_int32), ("blur_kernel_size", C.c_int32)]
 
 
 class Profile(C.Structure):

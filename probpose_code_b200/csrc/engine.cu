@@ -66,6 +66,7 @@ struct pp_engine {
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
   size_t g_stride = 0;  // bytes between the per-branch tap-gather buffers
+  bool branches = false;  // ProbMapHead: the four scalar branches exist (HeatmapHead: heatmap stack only)
 
   // packed weights (byte offsets)
   size_t w_patch;
@@ -103,6 +104,7 @@ static size_t plan(pp_engine* e) {
   e->tokens = e->gh * e->gw;
   e->D = c.embed_dim; e->FF = c.ffn_dim; e->heads = c.heads; e->dh = c.heads ? c.embed_dim / c.heads : 0;
   e->depth = c.depth; e->K = c.num_keypoints; e->DC = c.deconv_channels;
+  e->branches = c.deconv_channels > 0 && c.head_kind == PP_HEAD_PROBMAP;
   e->PK = 3 * c.patch * c.patch;
   e->max_b2 = 2 * c.max_batch;
   e->params.clear();
@@ -137,7 +139,7 @@ static size_t plan(pp_engine* e) {
     }
     add_param(e, b, "head.final_layer.weight", (int64_t)K * DC, 1);
     add_param(e, b, "head.final_layer.bias", K, 1);
-    for (int br = 0; br < 4; ++br) {
+    for (int br = 0; br < (e->branches ? 4 : 0); ++br) {
       const std::string p = std::string("head.") + kBranches[br] + "_layers.";
       for (int j = 0; j < 3; ++j) {
         add_param(e, b, p + std::to_string(4 * j) + ".weight", (int64_t)D * D * 9, 1);
@@ -169,18 +171,22 @@ static size_t plan(pp_engine* e) {
       e->dc_shift[i] = b.take(DC * sizeof(float));
     }
     e->w_final = b.take(pp_operand_bytes(prec, K, DC));
-    e->w_c1 = b.take(pp_operand_bytes(prec, 4 * D, 9 * D));
-    for (int br = 0; br < 4; ++br) {
-      e->w_c2[br] = b.take(pp_operand_bytes(prec, D, 9 * D));
-      e->w_c3[br] = b.take(pp_operand_bytes(prec, D, 9 * D));
+    size_t tmp_floats = (size_t)DC * 4 * (D > DC ? D : DC);  // one deconv phase matrix
+    if (e->branches) {
+      e->w_c1 = b.take(pp_operand_bytes(prec, 4 * D, 9 * D));
+      for (int br = 0; br < 4; ++br) {
+        e->w_c2[br] = b.take(pp_operand_bytes(prec, D, 9 * D));
+        e->w_c3[br] = b.take(pp_operand_bytes(prec, D, 9 * D));
+      }
+      for (int j = 0; j < 3; ++j) {
+        e->c_scale[j] = b.take((size_t)4 * D * sizeof(float));
+        e->c_shift[j] = b.take((size_t)4 * D * sizeof(float));
+      }
+      e->tail_w = b.take((size_t)4 * K * D * sizeof(float));
+      e->tail_b = b.take((size_t)4 * K * sizeof(float));
+      if ((size_t)4 * D * 9 * D > tmp_floats) tmp_floats = (size_t)4 * D * 9 * D;
     }
-    for (int j = 0; j < 3; ++j) {
-      e->c_scale[j] = b.take((size_t)4 * D * sizeof(float));
-      e->c_shift[j] = b.take((size_t)4 * D * sizeof(float));
-    }
-    e->tail_w = b.take((size_t)4 * K * D * sizeof(float));
-    e->tail_b = b.take((size_t)4 * K * sizeof(float));
-    e->pack_tmp = b.take((size_t)4 * D * 9 * D * sizeof(float));
+    e->pack_tmp = b.take(tmp_floats * sizeof(float));
   }
 
   // ---- activations ----
@@ -197,15 +203,17 @@ static size_t plan(pp_engine* e) {
   e->feat_bytes = pp_operand_bytes(prec, Mp0, D);
   e->feat_f32 = b.take((size_t)M * D * sizeof(float));
   if (DC > 0) {
-    e->g_stride = (pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 9 * D) + 1023) & ~size_t(1023);
-    e->g_op = b.take(4 * e->g_stride);  // tap gathers of the pooled 4x4 / 2x2 stages, one buffer per branch
     e->d1_op = b.take(pp_operand_bytes(prec, Mp1, DC));
     e->d1_bytes = pp_operand_bytes(prec, Mp1, DC);
     e->d2_op = b.take(pp_operand_bytes(prec, 16 * M, DC));
     e->logits = b.take((size_t)e->max_b2 * K * 16 * e->tokens * sizeof(float));
-    e->c_f32 = b.take((size_t)M * 4 * D * sizeof(float));
-    e->pool_op = b.take(pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 4 * D));
     e->scal = b.take((size_t)e->max_b2 * 4 * K * sizeof(float));
+    if (e->branches) {
+      e->g_stride = (pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 9 * D) + 1023) & ~size_t(1023);
+      e->g_op = b.take(4 * e->g_stride);  // tap gathers of the pooled 4x4 / 2x2 stages, one buffer per branch
+      e->c_f32 = b.take((size_t)M * 4 * D * sizeof(float));
+      e->pool_op = b.take(pp_operand_bytes(prec, (int64_t)16 * e->max_b2, 4 * D));
+    }
   }
   return b.off;
 }
@@ -230,6 +238,10 @@ static int validate_cfg(const pp_engine_cfg* c) {
                "tensor-core attention is built for 192 tokens (256x192 crops, patch 16, pad 2); this geometry has %d", tok);
   }
   PP_REQUIRE(c->depth > 0 || c->deconv_channels > 0, PP_ERR_INVALID, "engine has neither a backbone nor a head");
+  PP_REQUIRE(c->head_kind == PP_HEAD_PROBMAP || c->head_kind == PP_HEAD_HEATMAP, PP_ERR_INVALID, "bad head_kind %d", c->head_kind);
+  PP_REQUIRE(c->head_kind != PP_HEAD_HEATMAP || c->deconv_channels == 0 ||
+                 (c->blur_kernel_size >= 3 && c->blur_kernel_size <= 31 && (c->blur_kernel_size & 1)),
+             PP_ERR_INVALID, "HeatmapHead engine: blur_kernel_size %d must be odd and in [3, 31]", c->blur_kernel_size);
   if (c->deconv_channels > 0) {
     PP_REQUIRE(c->deconv_channels % 64 == 0, PP_ERR_UNSUPPORTED, "deconv_channels %d must be a multiple of 64",
                c->deconv_channels);
@@ -370,6 +382,7 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
     g.shift = e->P("head.final_layer.bias"); g.out_kind = PP_OUT_PLANES; g.plane = 16 * e->tokens; g.d = logits;
     PP_TRY(gemm(e, g, st));
   }
+  if (!e->branches) return PP_OK;  // HeatmapHead: the heatmap stack is the whole head
   // --- four scalar branches; the first conv of all four shares its input -> one GEMM, N = 4 D,
   // 9 taps over the zero-bordered feature map ---
   {
@@ -449,7 +462,7 @@ extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_
   }
   e->base = reinterpret_cast<uint8_t*>(workspace);
   e->bytes = workspace_bytes;
-  if (e->DC > 0 && getenv("PP_NO_BRANCH_STREAMS") == nullptr) {  // side streams of the scalar branches (no device memory involved)
+  if (e->branches && getenv("PP_NO_BRANCH_STREAMS") == nullptr) {  // side streams of the scalar branches (no device memory involved)
     bool ok = cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i)
       ok = cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess &&
@@ -533,7 +546,7 @@ extern "C" int pp_engine_finalize(pp_engine* e, void* stream) {
                             nullptr, e->cfg.bn_eps, DC, e->at<float>(e->dc_scale[i]), e->at<float>(e->dc_shift[i]), st));
     }
     PP_TRY(to_operand(e, e->P("head.final_layer.weight"), K, DC, e->w_final, st));
-    for (int br = 0; br < 4; ++br) {
+    for (int br = 0; br < (e->branches ? 4 : 0); ++br) {
       const std::string p = std::string("head.") + kBranches[br] + "_layers.";
       PP_TRY(launch_pack_conv3x3(e->P(p + "0.weight"), D, D, tmp + (size_t)br * D * 9 * D, st));
       for (int j = 0; j < 3; ++j) {
@@ -547,8 +560,8 @@ extern "C" int pp_engine_finalize(pp_engine* e, void* stream) {
       PP_CHECK_CUDA(cudaMemcpyAsync(e->at<float>(e->tail_b) + (size_t)br * K, e->P(p + "12.bias"), (size_t)K * sizeof(float),
                                     cudaMemcpyDeviceToDevice, st));
     }
-    PP_TRY(to_operand(e, tmp, 4 * D, 9 * D, e->w_c1, st));
-    for (int br = 0; br < 4; ++br) {
+    if (e->branches) PP_TRY(to_operand(e, tmp, 4 * D, 9 * D, e->w_c1, st));
+    for (int br = 0; br < (e->branches ? 4 : 0); ++br) {
       const std::string p = std::string("head.") + kBranches[br] + "_layers.";
       PP_TRY(launch_pack_conv3x3(e->P(p + "4.weight"), D, D, tmp, st));
       PP_TRY(to_operand(e, tmp, D, 9 * D, e->w_c2[br], st));
@@ -578,7 +591,7 @@ extern "C" int pp_engine_head(pp_engine* e, const float* feat_nchw, int32_t batc
                               void* stream) {
   PP_TRY(check_batch(e, batch, 1, "pp_engine_head"));
   PP_REQUIRE(e->head_ready, PP_ERR_STATE, "pp_engine_head: head weights not loaded / finalized");
-  PP_REQUIRE(batch == 0 || (feat_nchw && heat_logits && scalars), PP_ERR_INVALID, "pp_engine_head: NULL tensor");
+  PP_REQUIRE(batch == 0 || (feat_nchw && heat_logits && (scalars || !e->branches)), PP_ERR_INVALID, "pp_engine_head: NULL tensor");
   const int64_t before = g_launch_count;
   if (batch > 0) {
     PP_TRY(launch_nchw_to_operand(e->prec, feat_nchw, batch, e->tokens, e->D, e->at<>(e->feat_op), (cudaStream_t)stream, e->gh, e->gw));
@@ -604,6 +617,16 @@ extern "C" int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const 
     float* logits = e->at<float>(e->logits);
     float* scal = e->at<float>(e->scal);
     PP_TRY(run_head(e, passes * batch, logits, scal, st));
+    if (e->cfg.head_kind == PP_HEAD_HEATMAP) {  // HeatmapHead + UDPHeatmap: records are (B, K, 3)
+      pp_udp_cfg uc;
+      uc.num_keypoints = e->K; uc.height = 4 * e->gh; uc.width = 4 * e->gw; uc.blur_kernel_size = e->cfg.blur_kernel_size;
+      const size_t stride = (size_t)batch * e->K * 16 * e->tokens;
+      PP_TRY(timed(e, PP_KC_DECODE, st, [&] {
+        return pp_decode_udp(&uc, logits, flip_test ? logits + stride : nullptr, flip_indices, batch, records, merged_out, stream);
+      }));
+      e->last_launches = g_launch_count - before;
+      return PP_OK;
+    }
     pp_decode_cfg dc;
     dc.num_keypoints = e->K; dc.height = 4 * e->gh; dc.width = 4 * e->gw; dc.input_is_logits = 1;
     dc.temperature = e->cfg.temperature; dc.normalize = e->cfg.normalize; dc.error_divisor = 0.f;

@@ -32,11 +32,15 @@ class Engine:
                  patch_pad: int = 2, embed_dim: int = 384, depth: int = 12, heads: int = 12, ffn_dim: int = 1536,
                  num_keypoints: int = 17, deconv_channels: int = 256, ln_eps: float = 1e-6, bn_eps: float = 1e-5,
                  temperature: float = 0.5, normalize: float = 1.0, mean=PIXEL_MEAN, std=PIXEL_STD,
-                 device: Optional[torch.device] = None):
+                 head_kind: str = "probmap", blur_kernel_size: int = 11, device: Optional[torch.device] = None):
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        if head_kind not in ("probmap", "heatmap"):
+            raise ValueError(f'head_kind must be "probmap" (ProbMapHead) or "heatmap" (HeatmapHead), got {head_kind!r}')
         if not torch.cuda.is_available():
             raise _lib.PPError("probpose_code_b200 needs a CUDA device (sm_100a): there is no CPU path")
+        self.head_kind = head_kind
+        self.record_floats = _lib.RECORD_FLOATS if head_kind == "probmap" else 3
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.precision = precision
         self.max_batch = int(max_batch)
@@ -48,7 +52,8 @@ class Engine:
         self.cfg = _lib.EngineCfg(_lib.PRECISIONS[precision], self.max_batch, self.img_h, self.img_w, patch, patch_pad,
                                   embed_dim, depth, heads, ffn_dim, num_keypoints, deconv_channels, ln_eps, bn_eps,
                                   temperature, 1.0 if normalize is None else float(normalize),
-                                  (C.c_float * 3)(*mean), (C.c_float * 3)(*std))
+                                  (C.c_float * 3)(*mean), (C.c_float * 3)(*std),
+                                  _lib.HEAD_PROBMAP if head_kind == "probmap" else _lib.HEAD_HEATMAP, int(blur_kernel_size))
         nbytes = lib().pp_engine_workspace_bytes(C.byref(self.cfg))
         if nbytes == 0:
             check(-1, "pp_engine_workspace_bytes")
@@ -106,28 +111,30 @@ class Engine:
         return out
 
     def head(self, feat: torch.Tensor):
-        """featmap fp32 (B, C, gh, gw) -> (heatmap logits (B, K, 4gh, 4gw), scalars (B, 4, K))."""
+        """featmap fp32 (B, C, gh, gw) -> (heatmap logits (B, K, 4gh, 4gw), scalars (B, 4, K)); a HeatmapHead engine
+        returns the heatmaps (B, K, 4gh, 4gw) alone."""
         if not (feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous()):
             raise ValueError("feat must be a contiguous CUDA float32 tensor")
         if tuple(feat.shape[1:]) != (self.embed_dim, self.gh, self.gw):
             raise ValueError(f"feat must be (B, {self.embed_dim}, {self.gh}, {self.gw}), got {tuple(feat.shape)}")
         b = feat.shape[0]
         logits = torch.empty((b, self.num_keypoints, 4 * self.gh, 4 * self.gw), dtype=torch.float32, device=feat.device)
-        scal = torch.empty((b, 4, self.num_keypoints), dtype=torch.float32, device=feat.device)
+        scal = torch.empty((b, 4, self.num_keypoints), dtype=torch.float32, device=feat.device) if self.head_kind == "probmap" else None
         with torch.cuda.device(self.device):
-            check(lib().pp_engine_head(self._h, feat.data_ptr(), b, logits.data_ptr(), scal.data_ptr(), _stream()),
-                  "pp_engine_head")
-        return logits, scal
+            check(lib().pp_engine_head(self._h, feat.data_ptr(), b, logits.data_ptr(), None if scal is None else scal.data_ptr(),
+                                       _stream()), "pp_engine_head")
+        return (logits, scal) if scal is not None else logits
 
     def infer(self, crops: torch.Tensor, flip_test: bool = True, flip_indices: Sequence[int] = COCO_FLIP_INDICES,
               return_heatmaps: bool = False, out: Optional[torch.Tensor] = None):
         """End to end.  ``crops``: uint8 BGR (B, 3, H, W) (preprocessing fused) or fp32 normalised
         RGB.  Returns records (B, K, 7) fp32 [x_hm, y_hm, conf, prob, vis, oks, err / diag] and
-        optionally the merged normalised heatmaps (B, K, 4gh, 4gw)."""
+        optionally the merged normalised heatmaps (B, K, 4gh, 4gw).  HeatmapHead engine: records (B, K, 3) =
+        [x_hm, y_hm, score] (``pp_decode_udp``)."""
         is_u8 = crops.dtype == torch.uint8
         b = self._check_images(crops, torch.uint8 if is_u8 else torch.float32)
         k = self.num_keypoints
-        rec = out if out is not None else torch.empty((b, k, _lib.RECORD_FLOATS), dtype=torch.float32, device=crops.device)
+        rec = out if out is not None else torch.empty((b, k, self.record_floats), dtype=torch.float32, device=crops.device)
         merged = torch.empty((b, k, 4 * self.gh, 4 * self.gw), dtype=torch.float32, device=crops.device) if return_heatmaps else None
         fi = None
         if flip_test:

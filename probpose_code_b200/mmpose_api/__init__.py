@@ -5,9 +5,9 @@ Importing this package registers ``VisionTransformer`` (also as
 ``PoseDataPreprocessor`` in ``MODELS`` and ``ProbMap`` in ``KEYPOINT_CODECS`` - mmpose's own
 registries when mmpose is installed, a compatible stand-in otherwise."""
 from .backbone import VisionTransformer
-from .codec import BaseKeypointCodec, ProbMap
+from .codec import BaseKeypointCodec, ProbMap, UDPHeatmap
 from .estimator import PoseDataPreprocessor, TopdownPoseEstimator
-from .head import BaseHead, ProbMapHead
+from .head import BaseHead, HeatmapHead, ProbMapHead
 from .inference import TopdownAffine, inference_topdown
 from .registry import HAVE_MMPOSE, KEYPOINT_CODECS, MODELS, Registry
 from .structures import InstanceData, PixelData, PoseDataSample
@@ -35,6 +35,28 @@ def probpose_small_cfg(precision: str = None, flip_test: bool = True) -> dict:
                   oks_loss=dict(type="MSELoss", use_target_weight=True),
                   error_loss=dict(type="L1LogLoss", use_target_weight=True), detach_probability=True,
                   detach_visibility=True, normalize=1.0, freeze_error=True, freeze_oks=False, decoder=codec),
+        test_cfg=dict(flip_test=flip_test, flip_mode="heatmap", shift_heatmap=False),
+    )
+    if precision is not None:
+        cfg["precision"] = precision
+    return cfg
+
+
+def vitpose_cfg(arch: str = "base", precision: str = None, flip_test: bool = True) -> dict:
+    """``model = dict(...)`` of configs/body_2d_keypoint/topdown_heatmap/coco/td-hm_ViTPose-{small,base}_8xb64-210e_coco-256x192.py
+    (:40-75): ViT backbone + HeatmapHead + UDPHeatmap codec (SURVEY.md 8f rank 3 / BASELINE config 5)."""
+    dims = {"small": dict(embed_dims=384, num_layers=12, num_heads=12, feedforward_channels=384 * 4),
+            "base": dict(embed_dims=768, num_layers=12, num_heads=12, feedforward_channels=768 * 4)}[arch]
+    codec = dict(type="UDPHeatmap", input_size=(192, 256), heatmap_size=(48, 64), sigma=2)
+    cfg = dict(
+        type="TopdownPoseEstimator",
+        data_preprocessor=dict(type="PoseDataPreprocessor", mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375],
+                               bgr_to_rgb=True),
+        backbone=dict(type="mmpretrain.VisionTransformer", arch=dims, img_size=(256, 192), patch_size=16, qkv_bias=True,
+                      drop_path_rate=0.3 if arch == "base" else 0.1, with_cls_token=False, out_type="featmap",
+                      patch_cfg=dict(padding=2), init_cfg=None),
+        head=dict(type="HeatmapHead", in_channels=dims["embed_dims"], out_channels=17, deconv_out_channels=(256, 256),
+                  deconv_kernel_sizes=(4, 4), loss=dict(type="KeypointMSELoss", use_target_weight=True), decoder=codec),
         test_cfg=dict(flip_test=flip_test, flip_mode="heatmap", shift_heatmap=False),
     )
     if precision is not None:

@@ -1,5 +1,5 @@
-"""``ProbMap`` codec, decode side, on the GPU (mirrors mmpose/codecs/probmap.py and
-mmpose/codecs/base.py).  ``batch_decode`` is overridden, so ``BaseHead.decode`` takes its
+"""``ProbMap`` and ``UDPHeatmap`` codecs, decode side, on the GPU (mirror mmpose/codecs/probmap.py,
+mmpose/codecs/udp_heatmap.py and mmpose/codecs/base.py).  ``batch_decode`` is overridden, so ``BaseHead.decode`` takes its
 batched branch (base_head.py:57-62) and nothing round-trips through per-person numpy."""
 from __future__ import annotations
 
@@ -87,6 +87,57 @@ class ProbMap(BaseKeypointCodec):
 
     def batch_decode(self, batch_encoded: torch.Tensor) -> Tuple[List[np.ndarray], List[np.ndarray]]:
         """(B, K, H, W) CUDA tensor -> per-person lists, one kernel launch for the batch."""
+        rec = self._decode_device(batch_encoded)
+        kpts = self.keypoints_from_locs(rec[:, :, :2])
+        return [k[None] for k in kpts], [s[None] for s in rec[:, :, 2]]
+
+
+@register(KEYPOINT_CODECS, ["UDPHeatmap"])
+class UDPHeatmap(BaseKeypointCodec):
+    """Same constructor as the reference (udp_heatmap.py:70-98).  Only the ``"gaussian"`` heatmap type decodes
+    here (the ViTPose td-hm configs); ``encode`` builds training targets and is out of scope."""
+
+    label_mapping_table = dict(keypoint_weights="keypoint_weights")
+    field_mapping_table = dict(heatmaps="heatmaps")
+
+    def __init__(self, input_size: Tuple[int, int], heatmap_size: Tuple[int, int], heatmap_type: str = "gaussian",
+                 sigma: float = 2.0, radius_factor: float = 0.0546875, blur_kernel_size: int = 11) -> None:
+        super().__init__()
+        self.input_size = input_size
+        self.heatmap_size = heatmap_size
+        self.sigma = sigma
+        self.radius_factor = radius_factor
+        self.heatmap_type = heatmap_type
+        self.blur_kernel_size = blur_kernel_size
+        self.scale_factor = ((np.array(input_size) - 1) / (np.array(heatmap_size) - 1)).astype(np.float32)
+        if self.heatmap_type not in {"gaussian", "combined"}:
+            raise ValueError(f"{self.__class__.__name__} got invalid `heatmap_type` value"
+                             f"{self.heatmap_type}. Should be one of " '{"gaussian", "combined"}')
+
+    def encode(self, keypoints, keypoints_visible=None) -> dict:
+        raise NotImplementedError("UDPHeatmap.encode builds training targets; probpose_code_b200 covers inference only")
+
+    def keypoints_from_locs(self, locs: np.ndarray) -> np.ndarray:
+        """udp_heatmap.py:194-195: ``keypoints / [W - 1, H - 1] * input_size`` (float64)."""
+        w, h = self.heatmap_size
+        return locs / [w - 1, h - 1] * self.input_size
+
+    def _decode_device(self, heatmaps: torch.Tensor) -> np.ndarray:
+        if self.heatmap_type != "gaussian":
+            raise NotImplementedError('only heatmap_type="gaussian" is implemented on the GPU')
+        w, h = self.heatmap_size
+        assert heatmaps.dim() == 4 and tuple(heatmaps.shape[-2:]) == (h, w), (
+            f"heatmaps must be (B, K, {h}, {w}), got {tuple(heatmaps.shape)}")
+        return ops.decode_udp(heatmaps.float().contiguous(), blur_kernel_size=self.blur_kernel_size).cpu().numpy()
+
+    def decode(self, encoded: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """(K, H, W) float32 heatmaps -> keypoints (1, K, 2) float64 in input pixels, scores (1, K) float32
+        (udp_heatmap.py:146-196)."""
+        assert isinstance(encoded, np.ndarray) and encoded.ndim == 3, "expects heatmaps in shape (K, H, W)"
+        rec = self._decode_device(torch.from_numpy(np.ascontiguousarray(encoded, np.float32)).cuda()[None])
+        return self.keypoints_from_locs(rec[:, :, :2]), rec[:, :, 2]
+
+    def batch_decode(self, batch_encoded: torch.Tensor) -> Tuple[List[np.ndarray], List[np.ndarray]]:
         rec = self._decode_device(batch_encoded)
         kpts = self.keypoints_from_locs(rec[:, :, :2])
         return [k[None] for k in kpts], [s[None] for s in rec[:, :, 2]]

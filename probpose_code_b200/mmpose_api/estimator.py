@@ -17,7 +17,7 @@ from torch import nn
 
 from ._engine_cache import EngineCache
 from .backbone import VisionTransformer
-from .head import ProbMapHead
+from .head import HeatmapHead, ProbMapHead
 from .registry import MODELS, register
 from .structures import PixelData
 
@@ -84,7 +84,7 @@ class TopdownPoseEstimator(nn.Module):
 
     # ---- fused engine -----------------------------------------------------------------
     def _fusable(self) -> bool:
-        return (isinstance(self.backbone, VisionTransformer) and self.with_head and isinstance(self.head, ProbMapHead)
+        return (isinstance(self.backbone, VisionTransformer) and self.with_head and isinstance(self.head, (ProbMapHead, HeatmapHead))
                 and not self.with_neck and self.head.decoder is not None
                 and self.backbone._cache.precision == self.head._cache.precision)
 
@@ -92,8 +92,8 @@ class TopdownPoseEstimator(nn.Module):
         if self._fused is None:
             kw = dict(self.backbone._cache.kwargs)
             hk = self.head._cache.kwargs
-            kw.update(num_keypoints=hk["num_keypoints"], deconv_channels=hk["deconv_channels"],
-                      temperature=hk["temperature"], normalize=hk["normalize"])
+            kw.update({k: hk[k] for k in ("num_keypoints", "deconv_channels", "temperature", "normalize", "head_kind",
+                                          "blur_kernel_size") if k in hk})
             pre = self.data_preprocessor
             if getattr(pre, "mean_std", None):
                 kw.update(mean=pre.mean_std[0], std=pre.mean_std[1])

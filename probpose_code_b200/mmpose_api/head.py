@@ -211,3 +211,101 @@ class ProbMapHead(BaseHead):
 
     def loss(self, feats, batch_data_samples, train_cfg: dict = {}):
         raise NotImplementedError("training (ProbMapHead.loss) is out of scope of the B200 inference path")
+
+
+@register(MODELS, ["HeatmapHead"])
+class HeatmapHead(BaseHead):
+    """``HeatmapHead`` of the ViTPose td-hm configs (mmpose/models/heads/heatmap_heads/heatmap_head.py:22-268) with the
+    reference's constructor and ``state_dict`` layout (``deconv_layers.{0,1,3,4}``, ``final_layer``), inference side
+    only: the deconv stack runs on the same tcgen05 implicit-GEMM kernels as ProbMapHead's heatmap branch, flip merge
+    and the UDPHeatmap (DARK-UDP) decode in one kernel (``pp_decode_udp``)."""
+
+    _version = 2
+
+    def __init__(self, in_channels: Union[int, Sequence[int]], out_channels: int, deconv_out_channels=(256, 256, 256),
+                 deconv_kernel_sizes=(4, 4, 4), conv_out_channels=None, conv_kernel_sizes=None,
+                 final_layer: dict = dict(kernel_size=1), loss=None, decoder=None, init_cfg=None, precision: str = None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.test_cfg = {}
+        self.decoder = KEYPOINT_CODECS.build(decoder) if decoder is not None else None
+        if deconv_out_channels:
+            if deconv_kernel_sizes is None or len(deconv_out_channels) != len(deconv_kernel_sizes):
+                raise ValueError('"deconv_out_channels" and "deconv_kernel_sizes" should '
+                                 "be integer sequences with the same length. Got "
+                                 f"mismatched lengths {deconv_out_channels} and {deconv_kernel_sizes}")  # heatmap_head.py:83-88
+        unsupported = []
+        if not isinstance(in_channels, int): unsupported.append("multi-level in_channels")
+        if not deconv_out_channels or len(deconv_out_channels) != 2 or len(set(deconv_out_channels)) != 1:
+            unsupported.append(f"deconv_out_channels={deconv_out_channels} (two equal deconv layers)")
+        elif tuple(deconv_kernel_sizes) != (4, 4): unsupported.append(f"deconv_kernel_sizes={deconv_kernel_sizes} ((4, 4))")
+        if conv_out_channels: unsupported.append("conv_out_channels")
+        if final_layer is None or dict(final_layer).get("kernel_size", 1) != 1: unsupported.append("final layer != 1x1 conv")
+        if unsupported:
+            raise NotImplementedError("probpose_code_b200 HeatmapHead covers the shipped ViTPose td-hm configuration only; "
+                                      "unsupported: " + ", ".join(unsupported))
+        layers, c = [], in_channels
+        for co in deconv_out_channels:  # heatmap_head.py:141-173: k4 s2 p1 output_padding 0, no bias
+            layers += [nn.ConvTranspose2d(c, co, 4, 2, 1, 0, bias=False), nn.BatchNorm2d(co), nn.ReLU(inplace=True)]
+            c = co
+        self.deconv_layers = nn.Sequential(*layers)
+        self.conv_layers = nn.Identity()
+        self.final_layer = nn.Conv2d(c, out_channels, 1)
+        for m in self.modules():  # heatmap_head.py:189-195
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad_(False)
+        blur = getattr(self.decoder, "blur_kernel_size", 11)
+        self._cache = EngineCache(dict(embed_dim=in_channels, depth=0, heads=0, ffn_dim=0, num_keypoints=out_channels,
+                                       deconv_channels=deconv_out_channels[0], head_kind="heatmap", blur_kernel_size=blur),
+                                  precision)
+        self._named = None
+
+    engine_tensors = ProbMapHead.engine_tensors
+    check_test_cfg = staticmethod(ProbMapHead.check_test_cfg)
+
+    @torch.no_grad()
+    def forward(self, feats: Tuple[torch.Tensor]) -> torch.Tensor:
+        """heatmap_head.py:197-214: featmap -> heatmaps (B, K, 64, 48)."""
+        x = feats[-1]
+        eng = self._cache.get(self.engine_tensors(), x.shape[0], x.device)
+        return eng.head(x.float().contiguous())
+
+    def pack_records(self, records: torch.Tensor) -> List[InstanceData]:
+        """Device records (B, K, 3) -> per-person ``InstanceData(keypoints, keypoint_scores)`` (base_head.py:79-84)."""
+        rec = records.detach().cpu().numpy()
+        codec = self.decoder
+        if codec is None or not hasattr(codec, "keypoints_from_locs"):
+            raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__} (UDPHeatmap codec required)")
+        kpts = codec.keypoints_from_locs(rec[:, :, :2])
+        return [InstanceData(keypoints=kpts[i][None], keypoint_scores=rec[i, :, 2][None]) for i in range(rec.shape[0])]
+
+    @torch.no_grad()
+    def predict(self, feats, batch_data_samples, test_cfg: dict = {}):
+        """heatmap_head.py:216-265: flip merge + decode in one kernel over both passes' heatmaps."""
+        self.check_test_cfg(test_cfg)
+        want_hm = bool(test_cfg.get("output_heatmaps", False))
+        blur = getattr(self.decoder, "blur_kernel_size", 11)
+        if test_cfg.get("flip_test", False):
+            assert isinstance(feats, list) and len(feats) == 2
+            flip_indices = batch_data_samples[0].metainfo["flip_indices"]
+            x, xf = feats[0][-1], feats[1][-1]
+            b = x.shape[0]
+            hm = self.forward((torch.cat([x, xf], 0),))
+            out = ops.decode_udp(hm[:b], hm[b:], flip_indices, blur_kernel_size=blur, return_heatmaps=want_hm)
+        else:
+            out = ops.decode_udp(self.forward(feats), blur_kernel_size=blur, return_heatmaps=want_hm)
+        if want_hm:
+            records, heatmaps = out
+            return self.pack_records(records), [PixelData(heatmaps=h) for h in heatmaps.detach()]
+        return self.pack_records(out)
+
+    def loss(self, feats, batch_data_samples, train_cfg: dict = {}):
+        raise NotImplementedError("training (HeatmapHead.loss) is out of scope of the B200 inference path")
