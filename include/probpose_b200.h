@@ -174,6 +174,22 @@ PP_API int pp_decode_udp(const pp_udp_cfg* cfg, const float* maps, const float* 
                          int32_t batch, float* records, float* merged_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Heatmap read-back: per-person inverse warp of the heatmaps into the (padded) image and the
+ * element-wise max over the persons, in one pass.  Replaces, per person on the host in the reference,
+ *   revert_heatmap      mmpose/structures/utils.py:146-175  (cv2.warpAffine of the (H, W, K) float heatmap, INTER_LINEAR)
+ *   merge_data_samples  mmpose/structures/utils.py:117       (np.max over the per-person full-image tensors)
+ *  heatmaps    device fp32 (P, K, H, W)
+ *  warp_mats   device fp64 (P, 2, 3): the matrices revert_heatmap passes to cv2.warpAffine (heatmap -> image,
+ *              get_warp_matrix(..., inv=True), transforms.py:362-425), computed by the caller as the reference does
+ *  out         device fp32 (K, img_h, img_w)
+ *  scratch     device fp64 (P, 6) work space (the inverted matrices)
+ * Bit-identical to OpenCV's CV_32F warpAffine (fixed-point coordinates, 1/32-pixel float weights, BORDER_CONSTANT 0).
+ * ---------------------------------------------------------------------------------- */
+PP_API int pp_revert_heatmaps(const float* heatmaps, const double* warp_mats, int32_t persons, int32_t num_keypoints,
+                              int32_t height, int32_t width, float* out, int32_t img_h, int32_t img_w, double* scratch,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Global multi-head self-attention of one ViT layer on the tensor cores.  Replaces
  * mmpretrain 1.2.0 MultiheadAttention.forward between its qkv and proj Linears:
  *   q, k, v = qkv.reshape(B, N, 3, heads, d_h).permute(2, 0, 3, 1, 4)

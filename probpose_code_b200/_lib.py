@@ -23,7 +23,7 @@ EXPORTS = [
     "pp_last_error", "pp_version", "pp_decode", "pp_gemm", "pp_operand_bytes", "pp_operand_from_f32",
     "pp_engine_workspace_bytes", "pp_engine_create", "pp_engine_destroy", "pp_engine_load", "pp_engine_finalize",
     "pp_engine_backbone", "pp_engine_head", "pp_engine_infer", "pp_engine_last_launch_count",
-    "pp_engine_profile_begin", "pp_engine_profile_end", "pp_crop_warp", "pp_attention", "pp_decode_udp",
+    "pp_engine_profile_begin", "pp_engine_profile_end", "pp_crop_warp", "pp_attention", "pp_decode_udp", "pp_revert_heatmaps",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "decode", "other")
 
@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
                                C.c_int32, C.c_void_p]
     l.pp_decode_udp.argtypes = [C.POINTER(UdpCfg), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p]
+    l.pp_revert_heatmaps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_int32, C.c_void_p, C.c_void_p]
     l.pp_attention.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                C.c_void_p]
     if True:

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libprobpose_b200.so")
-SOURCES = ["capi.cu", "decode.cu", "decode_udp.cu", "gemm.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "vit_ops.cu", "head_ops.cu", "crop.cu", "engine.cu"]
+SOURCES = ["capi.cu", "decode.cu", "decode_udp.cu", "gemm.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "vit_ops.cu", "head_ops.cu", "crop.cu", "revert.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

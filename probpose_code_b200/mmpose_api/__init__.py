@@ -11,6 +11,7 @@ from .head import BaseHead, HeatmapHead, ProbMapHead
 from .inference import TopdownAffine, inference_topdown
 from .registry import HAVE_MMPOSE, KEYPOINT_CODECS, MODELS, Registry
 from .structures import InstanceData, PixelData, PoseDataSample
+from .utils import get_warp_matrix, merge_data_samples, revert_heatmap
 
 COCO_FLIP_INDICES = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]  # configs/_base_/datasets/coco.py:14-30
 

@@ -148,6 +148,26 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
     return out
 
 
+def revert_heatmaps(heatmaps: torch.Tensor, warp_mats, img_shape) -> torch.Tensor:
+    """``pp_revert_heatmaps``: heatmaps fp32 CUDA (P, K, H, W) + the (P, 2, 3) float64 heatmap -> image matrices of
+    ``revert_heatmap`` -> the max over persons of the warped maps, fp32 (K, img_h, img_w) (structures/utils.py:117,146-175)."""
+    _need_cuda(heatmaps, "heatmaps")
+    if heatmaps.dim() != 4:
+        raise ValueError(f"heatmaps must be (P, K, H, W), got {tuple(heatmaps.shape)}")
+    p, k, h, w = heatmaps.shape
+    mats = torch.as_tensor(warp_mats, dtype=torch.float64).reshape(-1, 2, 3)
+    if mats.shape[0] != p:
+        raise ValueError("one warp matrix per person")
+    mats = mats.to(heatmaps.device).contiguous()
+    img_h, img_w = int(img_shape[0]), int(img_shape[1])
+    out = torch.empty((k, img_h, img_w), dtype=torch.float32, device=heatmaps.device)
+    scratch = torch.empty((max(p, 1), 6), dtype=torch.float64, device=heatmaps.device)
+    with torch.cuda.device(heatmaps.device):
+        check(lib().pp_revert_heatmaps(heatmaps.data_ptr(), mats.data_ptr(), p, k, h, w, out.data_ptr(), img_h, img_w,
+                                       scratch.data_ptr(), _stream()), "pp_revert_heatmaps")
+    return out
+
+
 def attention(qkv_op: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int, precision: int, impl: int = 0,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``pp_attention``: softmax(Q K^T d_h^-0.5) V per (image, head) on the tensor cores.  ``qkv_op`` is the operand
