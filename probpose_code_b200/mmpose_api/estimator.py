@@ -175,11 +175,20 @@ class TopdownPoseEstimator(nn.Module):
         out = eng.infer(inputs, flip_test=flip, flip_indices=flip_indices, return_heatmaps=want_hm)
         records, heatmaps = out if want_hm else (out, None)
         fields = [PixelData(heatmaps=hm) for hm in heatmaps] if want_hm else None
-        return self.add_pred_to_datasample(self.head.pack_records(records), fields, data_samples)
+        if cfg.get("output_keypoint_indices", None) is not None:
+            return self.add_pred_to_datasample(self.head.pack_records(records), fields, data_samples)
+        # topdown.py:165-167 for the whole batch at once (same float arithmetic per element as the per-person loop)
+        meta = [d.metainfo for d in data_samples]
+        size = np.stack([m["input_size"] for m in meta])[:, None]
+        scale = np.stack([m["input_scale"] for m in meta])[:, None]
+        center = np.stack([m["input_center"] for m in meta])[:, None]
+        preds = self.head.pack_records(records, to_image=lambda k: k / size * scale + center - 0.5 * scale)
+        return self.add_pred_to_datasample(preds, fields, data_samples, mapped=True)
 
     def add_pred_to_datasample(self, batch_pred_instances: list, batch_pred_fields: Optional[list],
-                               batch_data_samples: list) -> list:
-        """topdown.py:128-194: input space -> image space, copy the bbox fields."""
+                               batch_data_samples: list, mapped: bool = False) -> list:
+        """topdown.py:128-194: input space -> image space, copy the bbox fields.  ``mapped``: the keypoints are
+        already in image space (the fused path maps the whole batch in one step)."""
         assert len(batch_pred_instances) == len(batch_data_samples)
         if batch_pred_fields is None:
             batch_pred_fields = []
@@ -189,11 +198,13 @@ class TopdownPoseEstimator(nn.Module):
             if pred_instances is None:
                 continue
             gt_instances = data_sample.gt_instances
-            input_center = data_sample.metainfo["input_center"]
-            input_scale = data_sample.metainfo["input_scale"]
-            input_size = data_sample.metainfo["input_size"]
-            pred_instances.keypoints[..., :2] = (pred_instances.keypoints[..., :2] / input_size * input_scale
-                                                 + input_center - 0.5 * input_scale)
+            if not mapped:
+                input_center = data_sample.metainfo["input_center"]
+                input_scale = data_sample.metainfo["input_scale"]
+                input_size = data_sample.metainfo["input_size"]
+            if not mapped:
+                pred_instances.keypoints[..., :2] = (pred_instances.keypoints[..., :2] / input_size * input_scale
+                                                     + input_center - 0.5 * input_scale)
             if "keypoints_visible" not in pred_instances:
                 pred_instances.keypoints_visible = pred_instances.keypoint_scores
             if output_keypoint_indices is not None:

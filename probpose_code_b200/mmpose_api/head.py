@@ -158,26 +158,25 @@ class ProbMapHead(BaseHead):
     def forward_heatmap(self, x: torch.Tensor) -> torch.Tensor:
         return self.forward((x,))[0]
 
-    def pack_records(self, records: torch.Tensor) -> List[InstanceData]:
+    def pack_records(self, records: torch.Tensor, to_image=None) -> List[InstanceData]:
         """Device records (B, K, 7) -> the reference's per-person ``InstanceData``
-        (probmap_head.py:776-798), with ONE device->host copy for the batch."""
+        (probmap_head.py:776-798), with ONE device->host copy for the batch.  ``to_image``: optional callable
+        mapping the whole batch's input-space keypoints (B, K, 2) to image space in one vectorised step (the
+        estimator's topdown.py:165-167 arithmetic); the per-person arrays are views of the batch arrays."""
         rec = records.detach().cpu().numpy()
         codec = self.decoder
         if codec is None or not hasattr(codec, "keypoints_from_locs"):
             raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__} (ProbMap codec required)")
         kpts = codec.keypoints_from_locs(rec[:, :, :2])
-        preds = []
-        for i in range(rec.shape[0]):
-            p = InstanceData(keypoints=kpts[i][None], keypoint_scores=rec[i, :, 2][None])
-            p.set_field(p["keypoint_scores"], "keypoints_conf")
-            p.set_field(rec[i, :, 3][None], "keypoints_probs")
-            p.set_field(rec[i, :, 4][None], "keypoints_visible")
-            p.set_field(rec[i, :, 5][None], "keypoints_oks")
-            p.set_field(rec[i, :, 6][None], "keypoints_error")
-            if not self.freeze_oks:  # probmap_head.py:796-798
-                p.set_field(rec[i, :, 5][None], "keypoint_scores")
-            preds.append(p)
-        return preds
+        if to_image is not None:
+            kpts = to_image(kpts)
+        cols = np.ascontiguousarray(rec[:, :, 2:].transpose(2, 0, 1))[:, :, None]  # (5, B, 1, K)
+        conf, prob, vis, oks, err = cols
+        scores = conf if self.freeze_oks else oks  # probmap_head.py:796-798
+        kpts = kpts[:, None]
+        return [InstanceData(keypoints=kpts[i], keypoint_scores=scores[i], keypoints_conf=conf[i], keypoints_probs=prob[i],
+                             keypoints_visible=vis[i], keypoints_oks=oks[i], keypoints_error=err[i])
+                for i in range(rec.shape[0])]
 
     @staticmethod
     def check_test_cfg(test_cfg: dict) -> None:
@@ -278,14 +277,18 @@ class HeatmapHead(BaseHead):
         eng = self._cache.get(self.engine_tensors(), x.shape[0], x.device)
         return eng.head(x.float().contiguous())
 
-    def pack_records(self, records: torch.Tensor) -> List[InstanceData]:
-        """Device records (B, K, 3) -> per-person ``InstanceData(keypoints, keypoint_scores)`` (base_head.py:79-84)."""
+    def pack_records(self, records: torch.Tensor, to_image=None) -> List[InstanceData]:
+        """Device records (B, K, 3) -> per-person ``InstanceData(keypoints, keypoint_scores)`` (base_head.py:79-84);
+        ``to_image`` as in :meth:`ProbMapHead.pack_records`."""
         rec = records.detach().cpu().numpy()
         codec = self.decoder
         if codec is None or not hasattr(codec, "keypoints_from_locs"):
             raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__} (UDPHeatmap codec required)")
         kpts = codec.keypoints_from_locs(rec[:, :, :2])
-        return [InstanceData(keypoints=kpts[i][None], keypoint_scores=rec[i, :, 2][None]) for i in range(rec.shape[0])]
+        if to_image is not None:
+            kpts = to_image(kpts)
+        kpts, scores = kpts[:, None], np.ascontiguousarray(rec[:, :, 2])[:, None]
+        return [InstanceData(keypoints=kpts[i], keypoint_scores=scores[i]) for i in range(rec.shape[0])]
 
     @torch.no_grad()
     def predict(self, feats, batch_data_samples, test_cfg: dict = {}):
