@@ -182,7 +182,7 @@ PP_API int pp_decode_udp(const pp_udp_cfg* cfg, const float* maps, const float* 
  *  warp_mats   device fp64 (P, 2, 3): the matrices revert_heatmap passes to cv2.warpAffine (heatmap -> image,
  *              get_warp_matrix(..., inv=True), transforms.py:362-425), computed by the caller as the reference does
  *  out         device fp32 (K, img_h, img_w)
- *  scratch     device fp64 (P, 6) work space (the inverted matrices)
+ *  scratch     device fp64 (P, 10) work space (the inverted matrices and each person's output rectangle)
  * Bit-identical to OpenCV's CV_32F warpAffine (fixed-point coordinates, 1/32-pixel float weights, BORDER_CONSTANT 0).
  * ---------------------------------------------------------------------------------- */
 PP_API int pp_revert_heatmaps(const float* heatmaps, const double* warp_mats, int32_t persons, int32_t num_keypoints,

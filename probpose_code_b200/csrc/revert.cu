@@ -21,11 +21,27 @@ constexpr int kRevThreads = 128;
 constexpr int kRevMaxK = PP_MAX_KEYPOINTS;
 
 // inverse matrices (dst -> src), computed once per person by a tiny kernel exactly like cv::warpAffine does
-__global__ void revert_invert_kernel(const double* __restrict__ mats, int n, double* __restrict__ inv) {
+// plus, per person, the output rectangle outside which every sample is the border value (the heatmap's corners
+// (-1 .. W, -1 .. H) mapped forward, 2 px of margin): pixels outside skip the exact coordinate arithmetic
+constexpr int kRevScratch = 10;  // doubles per person: 6 matrix entries + x0, x1, y0, y1
+__global__ void revert_invert_kernel(const double* __restrict__ mats, int n, int hh, int hw, double* __restrict__ inv) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   double m[6];
   for (int i = 0; i < 6; ++i) m[i] = mats[p * 6 + i];
+  {
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int c = 0; c < 4; ++c) {
+      const double hx = (c & 1) ? (double)hw : -1.0, hy = (c & 2) ? (double)hh : -1.0;
+      const double ix = m[0] * hx + m[1] * hy + m[2], iy = m[3] * hx + m[4] * hy + m[5];
+      x0 = fmin(x0, ix); x1 = fmax(x1, ix); y0 = fmin(y0, iy); y1 = fmax(y1, iy);
+    }
+    const bool finite = isfinite(x0) && isfinite(x1) && isfinite(y0) && isfinite(y1) && (m[0] * m[4] - m[1] * m[3]) != 0.0;
+    inv[p * kRevScratch + 6] = finite ? floor(x0) - 2.0 : -1e300;  // degenerate matrix: no rejection
+    inv[p * kRevScratch + 7] = finite ? ceil(x1) + 2.0 : 1e300;
+    inv[p * kRevScratch + 8] = finite ? floor(y0) - 2.0 : -1e300;
+    inv[p * kRevScratch + 9] = finite ? ceil(y1) + 2.0 : 1e300;
+  }
   double d = __dsub_rn(__dmul_rn(m[0], m[4]), __dmul_rn(m[1], m[3]));
   d = d != 0.0 ? __ddiv_rn(1.0, d) : 0.0;
   const double a11 = __dmul_rn(m[4], d), a22 = __dmul_rn(m[0], d);
@@ -33,7 +49,7 @@ __global__ void revert_invert_kernel(const double* __restrict__ mats, int n, dou
   const double b1 = __dsub_rn(__dmul_rn(-m[0], m[2]), __dmul_rn(m[1], m[5]));
   const double b2 = __dsub_rn(__dmul_rn(-m[3], m[2]), __dmul_rn(m[4], m[5]));
   m[2] = b1; m[5] = b2;
-  for (int i = 0; i < 6; ++i) inv[p * 6 + i] = m[i];
+  for (int i = 0; i < 6; ++i) inv[p * kRevScratch + i] = m[i];
 }
 
 template <int K>
@@ -47,7 +63,12 @@ __global__ void __launch_bounds__(kRevThreads) revert_merge_kernel(const float* 
   for (int k = 0; k < K; ++k) best[k] = -INFINITY;
   const size_t plane = (size_t)hh * hw;
   for (int p = 0; p < n; ++p) {
-    const double* m = inv + p * 6;  // uniform loads
+    const double* m = inv + p * kRevScratch;  // uniform loads
+    if ((double)x < m[6] || (double)x > m[7] || (double)y < m[8] || (double)y > m[9]) {  // far outside the footprint
+#pragma unroll
+      for (int k = 0; k < K; ++k) best[k] = fmaxf(best[k], 0.f);
+      continue;
+    }
     const int x0i = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
     const int y0i = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
     const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
@@ -91,7 +112,7 @@ extern "C" int pp_revert_heatmaps(const float* heatmaps, const double* warp_mats
   PP_REQUIRE(height > 0 && width > 0 && height < 32768 && width < 32768, PP_ERR_INVALID, "pp_revert_heatmaps: bad heatmap %dx%d", height, width);
   PP_REQUIRE(img_h > 0 && img_w > 0 && img_h <= 65535, PP_ERR_INVALID, "pp_revert_heatmaps: bad image %dx%d", img_h, img_w);
   cudaStream_t st = (cudaStream_t)stream;
-  revert_invert_kernel<<<(persons + 63) / 64, 64, 0, st>>>(warp_mats, persons, scratch);
+  revert_invert_kernel<<<(persons + 63) / 64, 64, 0, st>>>(warp_mats, persons, height, width, scratch);
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   const dim3 grid((img_w + kRevThreads - 1) / kRevThreads, img_h);

@@ -155,13 +155,14 @@ def revert_heatmaps(heatmaps: torch.Tensor, warp_mats, img_shape) -> torch.Tenso
     if heatmaps.dim() != 4:
         raise ValueError(f"heatmaps must be (P, K, H, W), got {tuple(heatmaps.shape)}")
     p, k, h, w = heatmaps.shape
-    mats = torch.as_tensor(warp_mats, dtype=torch.float64).reshape(-1, 2, 3)
+    import numpy as np
+    mats = torch.as_tensor(np.asarray(warp_mats, dtype=np.float64)).reshape(-1, 2, 3)
     if mats.shape[0] != p:
         raise ValueError("one warp matrix per person")
     mats = mats.to(heatmaps.device).contiguous()
     img_h, img_w = int(img_shape[0]), int(img_shape[1])
     out = torch.empty((k, img_h, img_w), dtype=torch.float32, device=heatmaps.device)
-    scratch = torch.empty((max(p, 1), 6), dtype=torch.float64, device=heatmaps.device)
+    scratch = torch.empty((max(p, 1), 10), dtype=torch.float64, device=heatmaps.device)
     with torch.cuda.device(heatmaps.device):
         check(lib().pp_revert_heatmaps(heatmaps.data_ptr(), mats.data_ptr(), p, k, h, w, out.data_ptr(), img_h, img_w,
                                        scratch.data_ptr(), _stream()), "pp_revert_heatmaps")

@@ -2,7 +2,7 @@
 """Micro-benchmarks of the individual kernels (CUDA events, L2 flushed between iterations).
 Writes one JSON line per case to stdout and gpurun_out/kernel_bench.jsonl.
 
-    python tools/kernel_bench.py decode gemm
+    python tools/kernel_bench.py decode udp gemm
 """
 import json
 import os
@@ -65,14 +65,41 @@ def bench_decode():
                       ("noise1e-3", lambda b, s: cases.noise_logits(b, s, 1e-3)),
                       ("noise1", lambda b, s: cases.noise_logits(b, s, 1.0))):
         for batch in (64, 256, 1024):
-            z = torch.from_numpy(gen(batch, 1)).cuda()
-            zf = torch.from_numpy(gen(batch, 2)).cuda()
+            if name == "planted":  # the flipped pass of a real model peaks at the mirrored place: consistent pair
+                z, zf = (torch.from_numpy(a).cuda() for a in cases.planted_peak_pair(batch, 1))
+            else:
+                z = torch.from_numpy(gen(batch, 1)).cuda()
+                zf = torch.from_numpy(gen(batch, 2)).cuda()
             for tta in (False, True):
                 fn = (lambda: ops.decode(z, zf, fi, input_is_logits=True)) if tta else (lambda: ops.decode(z, input_is_logits=True))
                 med, best = time_ms(fn)
                 nbytes = batch * (17 * 3072 * 4 * (2 if tta else 1) + 17 * 7 * 4)
                 emit(dict(kernel="decode", inputs=name, batch=batch, tta=tta, ms_median=med, ms_best=best,
                           gbs=nbytes / med / 1e6, frac_hbm=nbytes / med / 1e6 / HBM))
+
+
+def bench_udp_and_revert():
+    """the DARK-UDP decode and the heatmap read-back kernels."""
+    from oracle import revert_oracle, udp_oracle
+    fi = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]
+    for batch in (64, 256):
+        z = torch.from_numpy(udp_oracle.gaussian_heatmaps(batch, seed=1)).cuda()
+        zf = torch.from_numpy(udp_oracle.gaussian_heatmaps(batch, seed=2)).cuda()
+        for tta in (False, True):
+            fn = (lambda: ops.decode_udp(z, zf, fi)) if tta else (lambda: ops.decode_udp(z))
+            med, best = time_ms(fn)
+            nbytes = batch * (17 * 3072 * 4 * (2 if tta else 1) + 17 * 3 * 4)
+            emit(dict(kernel="decode_udp", batch=batch, tta=tta, ms_median=med, ms_best=best, gbs=nbytes / med / 1e6,
+                      frac_hbm=nbytes / med / 1e6 / HBM))
+    for persons, ih, iw in ((4, 720, 1280), (16, 1080, 1920)):
+        hms, centers, scales = revert_oracle.synthetic_people(5, persons, ih, iw)
+        mats = [revert_oracle.get_warp_matrix(c, s, 0, (48, 64), inv=True) for c, s in zip(centers, scales)]
+        t = torch.from_numpy(hms).cuda()
+        med, best = time_ms(lambda: ops.revert_heatmaps(t, mats, (ih, iw)))
+        nbytes = 17 * ih * iw * 4 + hms.nbytes
+        emit(dict(kernel="revert_heatmaps", persons=persons, image=f"{ih}x{iw}", ms_median=med, ms_best=best,
+                  gbs=nbytes / med / 1e6, frac_hbm=nbytes / med / 1e6 / HBM,
+                  note="algorithmic bytes = one write of the merged (17, H, W) tensor + one read of the heatmaps"))
 
 
 def bench_gemm():
@@ -107,5 +134,7 @@ if __name__ == "__main__":
     emit(dict(device=torch.cuda.get_device_name(0), peaks=dict(hbm_gbs=HBM, bf16_tflops=TF)))
     if "decode" in which:
         bench_decode()
+    if "udp" in which:
+        bench_udp_and_revert()
     if "gemm" in which:
         bench_gemm()
