@@ -96,30 +96,65 @@ __global__ void __launch_bounds__(kUdpThreads, 4) udp_decode_kernel(const __grid
   }
   if (lane == 0) { red_v[warp] = best; red_i[warp] = best_i; }
 
-  // ---- row pass of the blur: zero outside the map ----
+  // ---- row pass of the blur (zero outside the map), register-blocked: a thread owns RB consecutive outputs of one
+  // row and slides over RB + ntaps - 1 inputs held in registers - one shared-memory read per input, not per tap ----
   const int rad = p.ntaps >> 1;
-  for (int i = tid; i < NPX; i += kUdpThreads) {
-    const int y = i / W, x = i % W;
+  constexpr int RB = 12;                       // W / RB segments per row
+  static_assert(W % RB == 0 && (H * (W / RB)) % kUdpThreads == 0, "row segments must tile the block");
+  constexpr int kWin = RB + kUdpMaxTaps - 1;
+  for (int sgm = tid; sgm < H * (W / RB); sgm += kUdpThreads) {
+    const int y = sgm / (W / RB), x0 = (sgm % (W / RB)) * RB;
     const float* row = sP + y * W;
-    float acc = 0.f;
-    for (int j = 0; j < p.ntaps; ++j) {
-      const int xx = x + j - rad;
-      if (xx >= 0 && xx < W) acc = fmaf(row[xx], p.taps[j], acc);
+    float win[kWin];
+#pragma unroll
+    for (int i = 0; i < kWin; ++i) {
+      const int xx = x0 - rad + i;
+      win[i] = (i < RB + 2 * rad && xx >= 0 && xx < W) ? row[xx] : 0.f;
     }
-    sR[i] = acc;
+    float acc[RB];
+#pragma unroll
+    for (int o = 0; o < RB; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kUdpMaxTaps; ++j) {
+      if (j < p.ntaps) {  // block-uniform
+        const float t = p.taps[j];
+#pragma unroll
+        for (int o = 0; o < RB; ++o) acc[o] = fmaf(win[o + j], t, acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < RB; ++o) sR[y * W + x0 + o] = acc[o];
   }
   __syncthreads();
-  // ---- column pass, maximum of the blurred map ----
+  // ---- column pass, maximum of the blurred map: a thread owns CB consecutive rows of one column ----
   float bmax = -INFINITY;
-  for (int i = tid; i < NPX; i += kUdpThreads) {
-    const int y = i / W, x = i % W;
-    float acc = 0.f;
-    for (int j = 0; j < p.ntaps; ++j) {
-      const int yy = y + j - rad;
-      if (yy >= 0 && yy < H) acc = fmaf(sR[yy * W + x], p.taps[j], acc);
+  constexpr int CB = 16;
+  static_assert(H % CB == 0, "column segments");
+  constexpr int kWinC = CB + kUdpMaxTaps - 1;
+  for (int sgm = tid; sgm < W * (H / CB); sgm += kUdpThreads) {
+    const int x = sgm % W, y0 = (sgm / W) * CB;  // consecutive threads -> consecutive columns: conflict-free
+    float win[kWinC];
+#pragma unroll
+    for (int i = 0; i < kWinC; ++i) {
+      const int yy = y0 - rad + i;
+      win[i] = (i < CB + 2 * rad && yy >= 0 && yy < H) ? sR[yy * W + x] : 0.f;
     }
-    sC[i] = acc;
-    bmax = fmaxf(bmax, acc);
+    float acc[CB];
+#pragma unroll
+    for (int o = 0; o < CB; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kUdpMaxTaps; ++j) {
+      if (j < p.ntaps) {
+        const float t = p.taps[j];
+#pragma unroll
+        for (int o = 0; o < CB; ++o) acc[o] = fmaf(win[o + j], t, acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CB; ++o) {
+      sC[(y0 + o) * W + x] = acc[o];
+      bmax = fmaxf(bmax, acc[o]);
+    }
   }
   bmax = warp_max(bmax);
   if (lane == 0) red_b[warp] = bmax;
