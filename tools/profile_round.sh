@@ -14,4 +14,7 @@ for shape in qkv fc1 fc2; do
   ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 1 -c 1 -o $out/${tag}_gemm_$shape python tools/gemm_probe.py $shape fp16x3 2 > /dev/null 2>&1
 done
 python tools/vitb_bench.py > $out/${tag}_vitb_bench.jsonl 2>/dev/null
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"udp_decode|revert_merge" --csv --log-file $out/${tag}_udp_revert.csv python tools/kernel_bench.py udp > /dev/null 2>&1
+python tools/kernel_bench.py decode udp 2>/dev/null | grep -v Warn > $out/${tag}_kernel_bench.jsonl
+python bench.py --batch 1 --steps 50 --warmup 10 --no-cpu-baseline --no-decode-leg > $out/${tag}_bench_batch1.json 2>/dev/null
 ls -la $out | grep $tag
