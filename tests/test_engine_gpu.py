@@ -132,3 +132,17 @@ def test_vit_base_backbone(setup):
     eng = Engine(precision="fp16x3", max_batch=2, embed_dim=768, heads=12, ffn_dim=3072, deconv_channels=0)
     eng.load_state_dict(sd, prefixes=("backbone.",))
     assert _rel(eng.backbone(x.cuda().contiguous()), feat) <= STAGE_REL["fp16x3"]
+
+
+@pytest.mark.parametrize("flip", [True, False])
+def test_batch_invariance(setup, flip):
+    """Persons are independent units: a person's record must not depend on who else is in the batch, bit
+    for bit - the property the per-rank sharding relies on.  Also exercises single-crop calls (192 rows = 1.5 GEMM
+    tiles, attention tile 1 zero-filled beyond the last image)."""
+    from probpose_code_b200 import synth as s
+    eng = _engine("fp16x3", setup["sd"], )
+    crops = s.make_crops(4, seed=21).cuda()
+    full = eng.infer(crops, flip_test=flip).cpu()
+    for lo, hi in ((0, 1), (1, 3), (3, 4)):
+        part = eng.infer(crops[lo:hi].contiguous(), flip_test=flip).cpu()
+        assert torch.equal(part, full[lo:hi]), f"records of crops[{lo}:{hi}] depend on the batch composition"
