@@ -285,6 +285,19 @@ PP_API int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const floa
 /* Number of kernels the last pp_engine_* call launched (bench.py's gpu_launches). */
 PP_API int64_t pp_engine_last_launch_count(const pp_engine* e);
 
+/* CUDA-graph replay inside pp_engine_infer.  Everything between the patch extraction (which reads the
+ * caller's crops) and the decode (which writes the caller's records) touches the workspace only, so it
+ * is captured once per (batch, flip_test) shape - on the second call of that shape - and replayed with
+ * one cudaGraphLaunch on the caller's stream afterwards; results are bit-identical to plain launches.
+ * Used for calls of at most `max_images` images (flip_test counts twice); 0 switches it off, a negative
+ * value removes the limit.  Default 16 (117 launches per call: 0.76 ms of host time for a single crop, 0.02 ms replayed), or the
+ * PP_ENGINE_GRAPH environment variable.  While profiling (below) launches are always plain.
+ * The reference has no counterpart: mmengine's test_step issues eager PyTorch ops
+ * (mmpose/apis/inference.py:194-196). */
+PP_API int pp_engine_set_graph(pp_engine* e, int32_t max_images);
+/* Number of graph replays so far (tests assert the graph path actually ran). */
+PP_API int64_t pp_engine_graph_replay_count(const pp_engine* e);
+
 /* Per-kernel-class device timing (bench.py's roofline numbers).  Between _begin and _end
  * every kernel a pp_engine_* call launches is bracketed by a CUDA event pair on the caller's
  * stream; _end synchronises that stream and sums the elapsed times per class.  gemm_flops is

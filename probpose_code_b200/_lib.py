@@ -23,7 +23,7 @@ EXPORTS = [
     "pp_last_error", "pp_version", "pp_decode", "pp_gemm", "pp_operand_bytes", "pp_operand_from_f32",
     "pp_engine_workspace_bytes", "pp_engine_create", "pp_engine_destroy", "pp_engine_load", "pp_engine_finalize",
     "pp_engine_backbone", "pp_engine_head", "pp_engine_infer", "pp_engine_last_launch_count",
-    "pp_engine_profile_begin", "pp_engine_profile_end", "pp_crop_warp", "pp_attention", "pp_decode_udp", "pp_revert_heatmaps",
+    "pp_engine_profile_begin", "pp_engine_profile_end", "pp_engine_set_graph", "pp_engine_graph_replay_count", "pp_crop_warp", "pp_attention", "pp_decode_udp", "pp_revert_heatmaps",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "decode", "other")
 
@@ -107,6 +107,9 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         l.pp_engine_last_launch_count.restype = C.c_int64
         l.pp_engine_last_launch_count.argtypes = [C.c_void_p]
+        l.pp_engine_set_graph.argtypes = [C.c_void_p, C.c_int32]
+        l.pp_engine_graph_replay_count.restype = C.c_int64
+        l.pp_engine_graph_replay_count.argtypes = [C.c_void_p]
         l.pp_engine_profile_begin.argtypes = [C.c_void_p]
         l.pp_engine_profile_end.argtypes = [C.c_void_p, C.POINTER(Profile), C.c_void_p]
     _lib = l

@@ -65,6 +65,14 @@ struct pp_engine {
   // pooled-stage convolutions run concurrently on side streams (fork / join by events)
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  // CUDA-graph replay of the pointer-independent middle of pp_engine_infer (everything between the
+  // patch extraction, which reads the caller's crops, and the decode, which writes the caller's records):
+  // one captured graph per (batch, passes); see run_body_graphed
+  struct Graph { int batch, passes, seen; int64_t launches; cudaGraphExec_t exec; };
+  std::vector<Graph> graphs;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
+  int graph_max_images = 0;           // replay when passes * batch <= this; 0 = off, < 0 = no limit
+  int64_t graph_replays = 0;
   size_t g_stride = 0;  // bytes between the per-branch tap-gather buffers
   bool branches = false;  // ProbMapHead: the four scalar branches exist (HeatmapHead: heatmap stack only)
 
@@ -255,6 +263,10 @@ static int validate_cfg(const pp_engine_cfg* c) {
   return PP_OK;
 }
 
+// Calls of at most this many images (passes x batch) replay a captured graph by default (measured: 5-7 % less device
+// time and 40x less host time per call up to 16 images, neutral beyond: profiles/r01e_graph_bench.jsonl).
+constexpr int kGraphDefaultMaxImages = 16;
+
 static pp_gemm_args gemm_args(const pp_engine* e, int64_t m, int n, int k, const void* a, const void* w) {
   pp_gemm_args g = {};
   g.precision = e->prec; g.m = (int)m; g.n = n; g.k = k; g.a = a; g.w = w;
@@ -298,16 +310,21 @@ static int to_operand(const pp_engine* e, const float* src, int64_t rows, int64_
 }
 
 // ---- forward pieces ---------------------------------------------------------------------------
-static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int batch, int passes, bool want_f32,
-                        cudaStream_t st) {
-  const int D = e->D, FF = e->FF, prec = e->prec;
-  const int64_t M = (int64_t)passes * batch * e->tokens;
+// crops -> patch matrix (the only kernel of the backbone that reads caller memory)
+static int run_patchify(pp_engine* e, const uint8_t* u8, const float* xf, int batch, int passes, cudaStream_t st) {
+  const int prec = e->prec;
   PatchifyParams pp_;
   pp_.u8_bgr = u8; pp_.x_f32 = xf; pp_.batch = batch; pp_.passes = passes;
   pp_.img_h = e->cfg.img_h; pp_.img_w = e->cfg.img_w; pp_.patch = e->cfg.patch; pp_.pad = e->cfg.patch_pad;
   pp_.gh = e->gh; pp_.gw = e->gw;
   for (int c = 0; c < 3; ++c) { pp_.mean[c] = e->cfg.mean[c]; pp_.inv_std[c] = 1.0f / e->cfg.std[c]; }
-  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_patchify(prec, pp_, e->at<>(e->a_op), st); }));
+  return timed(e, PP_KC_OTHER, st, [&] { return launch_patchify(prec, pp_, e->at<>(e->a_op), st); });
+}
+
+// patch matrix -> features: workspace buffers only
+static int run_encoder(pp_engine* e, int batch, int passes, bool want_f32, cudaStream_t st) {
+  const int D = e->D, FF = e->FF, prec = e->prec;
+  const int64_t M = (int64_t)passes * batch * e->tokens;
   {
     pp_gemm_args g = gemm_args(e, M, D, e->PK, e->at<>(e->a_op), e->at<>(e->w_patch));
     g.shift = e->P("backbone.patch_embed.projection.bias");
@@ -427,6 +444,73 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
   return PP_OK;
 }
 
+static int run_backbone(pp_engine* e, const uint8_t* u8, const float* xf, int batch, int passes, bool want_f32,
+                        cudaStream_t st) {
+  PP_TRY(run_patchify(e, u8, xf, batch, passes, st));
+  return run_encoder(e, batch, passes, want_f32, st);
+}
+
+// The middle of pp_engine_infer: patch matrix -> logits + branch scalars, all inside the workspace.
+static int run_body(pp_engine* e, int batch, int passes, cudaStream_t st) {
+  PP_TRY(run_encoder(e, batch, passes, false, st));
+  return run_head(e, passes * batch, e->at<float>(e->logits), e->at<float>(e->scal), st);
+}
+
+static void graph_give_up(pp_engine* e) {  // capture is unavailable here: plain launches from now on
+  e->graph_max_images = 0;
+  cudaGetLastError();
+}
+
+// run_body through a CUDA graph: the first call of a (batch, passes) shape runs plainly (and finishes the
+// one-time function-attribute set-up of every launcher), the second one is captured on the engine's own
+// stream - kernel nodes keep their programmatic-dependent-launch edges, the branch side streams become
+// parallel branches of the graph - and every later call is ONE cudaGraphLaunch on the caller's stream.
+static int run_body_graphed(pp_engine* e, int batch, int passes, cudaStream_t st) {
+  const int64_t images = (int64_t)batch * passes;
+  if (e->profiling || e->graph_max_images == 0 || (e->graph_max_images > 0 && images > e->graph_max_images))
+    return run_body(e, batch, passes, st);
+  pp_engine::Graph* g = nullptr;
+  for (auto& it : e->graphs)
+    if (it.batch == batch && it.passes == passes) g = &it;
+  if (!g) {
+    if (e->graphs.size() >= 64) {  // a caller cycling through many shapes: drop the oldest graph
+      if (e->graphs.front().exec) cudaGraphExecDestroy(e->graphs.front().exec);
+      e->graphs.erase(e->graphs.begin());
+    }
+    e->graphs.push_back({batch, passes, 1, 0, nullptr});
+    return run_body(e, batch, passes, st);
+  }
+  if (!g->exec) {
+    if (!e->cap_stream && cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      graph_give_up(e);
+      return run_body(e, batch, passes, st);
+    }
+    if (cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      graph_give_up(e);
+      return run_body(e, batch, passes, st);
+    }
+    const int64_t c0 = g_launch_count;
+    const int rc = run_body(e, batch, passes, e->cap_stream);
+    const int64_t launches = g_launch_count - c0;
+    g_launch_count = c0;  // nothing has run yet: the replay below counts them
+    cudaGraph_t graph = nullptr;
+    cudaError_t err = cudaStreamEndCapture(e->cap_stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == PP_OK && err == cudaSuccess && graph) err = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != PP_OK || err != cudaSuccess || !exec) {
+      graph_give_up(e);
+      return run_body(e, batch, passes, st);
+    }
+    g->exec = exec;
+    g->launches = launches;
+  }
+  PP_CHECK_CUDA(cudaGraphLaunch(g->exec, st));
+  count_launch((int)g->launches);
+  ++e->graph_replays;
+  return PP_OK;
+}
+
 static int check_batch(const pp_engine* e, int batch, int passes, const char* what) {
   PP_REQUIRE(e != nullptr, PP_ERR_INVALID, "%s: engine is NULL", what);
   PP_REQUIRE(batch >= 0 && (int64_t)batch * passes <= e->max_b2, PP_ERR_INVALID,
@@ -473,12 +557,27 @@ extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_
       return PP_ERR_CUDA;
     }
   }
+  {  // graph replay of small calls is on by default; PP_ENGINE_GRAPH = 0 (off), -1 (every size) or a limit in images
+    const char* env = getenv("PP_ENGINE_GRAPH");
+    e->graph_max_images = env ? atoi(env) : kGraphDefaultMaxImages;
+  }
   *out = e;
   return PP_OK;
 }
 
+extern "C" int pp_engine_set_graph(pp_engine* e, int32_t max_images) {
+  PP_REQUIRE(e != nullptr, PP_ERR_INVALID, "pp_engine_set_graph: engine is NULL");
+  e->graph_max_images = max_images;
+  return PP_OK;
+}
+
+extern "C" int64_t pp_engine_graph_replay_count(const pp_engine* e) { return e ? e->graph_replays : 0; }
+
 extern "C" void pp_engine_destroy(pp_engine* e) {
   if (!e) return;
+  for (auto& g : e->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (auto& s : e->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
   if (e->fork_ev) cudaEventDestroy(e->fork_ev);
@@ -613,10 +712,10 @@ extern "C" int pp_engine_infer(pp_engine* e, const uint8_t* crops_u8_bgr, const 
   const int64_t before = g_launch_count;
   if (batch > 0) {
     cudaStream_t st = (cudaStream_t)stream;
-    PP_TRY(run_backbone(e, crops_u8_bgr, x_f32, batch, passes, false, st));
+    PP_TRY(run_patchify(e, crops_u8_bgr, x_f32, batch, passes, st));
     float* logits = e->at<float>(e->logits);
     float* scal = e->at<float>(e->scal);
-    PP_TRY(run_head(e, passes * batch, logits, scal, st));
+    PP_TRY(run_body_graphed(e, batch, passes, st));
     if (e->cfg.head_kind == PP_HEAD_HEATMAP) {  // HeatmapHead + UDPHeatmap: records are (B, K, 3)
       pp_udp_cfg uc;
       uc.num_keypoints = e->K; uc.height = 4 * e->gh; uc.width = 4 * e->gw; uc.blur_kernel_size = e->cfg.blur_kernel_size;

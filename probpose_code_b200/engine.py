@@ -150,6 +150,15 @@ class Engine:
     def last_launch_count(self) -> int:
         return int(lib().pp_engine_last_launch_count(self._h))
 
+    def set_graph(self, max_images: int) -> None:
+        """CUDA-graph replay of the workspace-only middle of :meth:`infer` for calls of at most
+        ``max_images`` images (flip counts twice); 0 = off, negative = no limit (``pp_engine_set_graph``)."""
+        check(lib().pp_engine_set_graph(self._h, int(max_images)), "pp_engine_set_graph")
+
+    @property
+    def graph_replay_count(self) -> int:
+        return int(lib().pp_engine_graph_replay_count(self._h))
+
     def profile_begin(self) -> None:
         check(lib().pp_engine_profile_begin(self._h), "pp_engine_profile_begin")
 

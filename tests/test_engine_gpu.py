@@ -146,3 +146,38 @@ def test_batch_invariance(setup, flip):
     for lo, hi in ((0, 1), (1, 3), (3, 4)):
         part = eng.infer(crops[lo:hi].contiguous(), flip_test=flip).cpu()
         assert torch.equal(part, full[lo:hi]), f"records of crops[{lo}:{hi}] depend on the batch composition"
+
+
+@pytest.mark.parametrize("flip", [True, False])
+def test_graph_replay_is_bit_identical(setup, flip):
+    """pp_engine_set_graph: the captured middle of pp_engine_infer (first call plain, second captured, later calls
+    one cudaGraphLaunch) must give the records of plain launches bit for bit, on fresh inputs at fresh addresses,
+    interleaved with another shape, and on a non-default stream."""
+    from probpose_code_b200 import synth as s
+    eng = _engine("fp16x3", setup["sd"])
+    batches = [s.make_crops(3, seed=40 + i).cuda() for i in range(5)]
+    other = s.make_crops(2, seed=50).cuda()
+    eng.set_graph(0)
+    plain = [eng.infer(c, flip_test=flip).cpu() for c in batches]
+    plain_other = eng.infer(other, flip_test=flip).cpu()
+    launches = eng.last_launch_count
+    assert eng.graph_replay_count == 0
+    eng.set_graph(-1)
+    for i, c in enumerate(batches):
+        got = eng.infer(c.clone(), flip_test=flip).cpu()
+        assert torch.equal(got, plain[i]), f"call {i} (graph path) differs from plain launches"
+        assert eng.last_launch_count == launches
+        if i == 1:
+            assert torch.equal(eng.infer(other, flip_test=flip).cpu(), plain_other)
+    assert eng.graph_replay_count == len(batches) - 1  # call 0 plain, call 1 captured + replayed, 2.. replayed
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        got = eng.infer(batches[0], flip_test=flip)
+    st.synchronize()
+    assert torch.equal(got.cpu(), plain[0])
+    eng.profile_begin()  # profiling brackets every launch with events: always plain launches
+    n = eng.graph_replay_count
+    got = eng.infer(batches[2], flip_test=flip).cpu()
+    prof = eng.profile_end()
+    assert eng.graph_replay_count == n and prof["gemm"]["launches"] > 0
+    assert torch.equal(got, plain[2])
