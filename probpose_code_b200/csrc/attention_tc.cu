@@ -3,7 +3,11 @@
 // Reference semantics: mmpretrain 1.2.0 MultiheadAttention.forward (see attention.cu) =
 //   softmax(Q K^T * d_h^-0.5) V per (image, head), Q / K / V = column blocks of the qkv GEMM output.
 //
-// One CTA (8 warps) per (image, head), two CTAs per SM; a query row = a TMEM lane is shared by two threads
+// PERSISTENT CTAs (8 warps), two per SM, each walking (image, head) units handed out by an atomic counter; the
+// next unit's Q / K tiles are requested as soon as the current unit's last S = Q K^T has completed and its V as soon
+// as the last P V has, so every load after the first hides behind the softmax / P V / read-out of the unit before
+// (single-buffered shared memory: 80 KB per CTA), and barrier set-up / TMEM allocation happen once per CTA.
+// A query row = a TMEM lane is shared by two threads
 // (warps w and w + 4 may access the same lane quarter) that split its 192 keys in halves:
 //   * TMA (cp.async.bulk.tensor, 64- / 128-byte swizzle) stages Q (two 128-row tiles: rows 0-127 and
 //     128-255, of which 128-191 are this image's), K and V straight out of the qkv operand,
@@ -25,6 +29,8 @@
 
 #include <math.h>
 
+#include <atomic>
+
 namespace pp {
 
 int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t row_elems, int box_rows, int box_cols,
@@ -34,6 +40,18 @@ namespace {
 
 constexpr int kTcThreads = 256;
 constexpr int kNTok = 192;
+constexpr int kSchedSlots = 64;
+__device__ unsigned g_att_sched[2 * kSchedSlots];  // zero-initialised; see launch_tc
+
+int num_sms_att() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -127,9 +145,9 @@ struct AttCfg {
   static constexpr int OFF_K = 2 * NOPS * Q_BYTES;
   static constexpr int OFF_V = OFF_K + NOPS * KV_BYTES;
   static constexpr int OFF_BAR = OFF_V + NOPS * KV_BYTES;
-  static constexpr int LOAD0_BYTES = NOPS * (Q_BYTES + KV_BYTES);  // Q tile 0 + K: what the first S needs
-  static constexpr int LOAD1_BYTES = NOPS * (Q_BYTES + KV_BYTES);  // Q tile 1 + V
-  static constexpr int OFF_X = OFF_BAR + 64;        // row max / row sum halves: float [2][2][128]
+  static constexpr int LOAD_QK_BYTES = NOPS * (2 * Q_BYTES + KV_BYTES);  // both Q tiles + K: free again after the unit's second S
+  static constexpr int LOAD_V_BYTES = NOPS * KV_BYTES;                   // V: free again after the unit's second P V
+  static constexpr int OFF_X = OFF_BAR + 64;        // row max / row sum halves: float [2][2][128]; next-unit mailbox at OFF_BAR + 48
   static constexpr int SMEM_BYTES = OFF_X + 2 * 2 * 128 * 4 + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 256;             // S / P: 192 columns, O: DH columns at 192
   static_assert(DH == 32 || DH == 64, "head width");
@@ -139,7 +157,7 @@ struct AttCfg {
 template <int DH, int SPLIT, bool BF16>
 __global__ void __launch_bounds__(kTcThreads, DH == 32 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const int heads,
-                    uint16_t* __restrict__ out_op) {
+                    const int units, unsigned* __restrict__ sched, uint16_t* __restrict__ out_op) {
   using Cfg = AttCfg<DH, SPLIT>;
   constexpr int NOPS = Cfg::NOPS, ROWB = Cfg::ROWB;
   extern __shared__ uint8_t att_raw[];
@@ -149,12 +167,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* s_bar = full_bar + 2;
   uint64_t* o_bar = full_bar + 3;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 4);
+  volatile int* next_box = reinterpret_cast<volatile int*>(full_bar + 6);  // thread 0 -> CTA: the unit after this one
   float* x_max = reinterpret_cast<float*>(smem + Cfg::OFF_X);  // [half][row]
   float* x_sum = x_max + 2 * 128;
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int D = heads * DH;
 
   if (threadIdx.x == 0) {
@@ -180,23 +198,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   auto sK = [&](int part) { return smem + Cfg::OFF_K + part * Cfg::KV_BYTES; };
   auto sV = [&](int part) { return smem + Cfg::OFF_V + part * Cfg::KV_BYTES; };
 
-  if (threadIdx.x == 0) {
-    ptx::mbar_arrive_expect_tx(full_bar, Cfg::LOAD0_BYTES);
-    ptx::mbar_arrive_expect_tx(full_bar1, Cfg::LOAD1_BYTES);
-    const int row0 = b * kNTok;
+  auto load_qk = [&](int unit) {  // thread 0
+    const int row0 = (unit / heads) * kNTok, hc = (unit % heads) * DH;
+    ptx::mbar_arrive_expect_tx(full_bar, Cfg::LOAD_QK_BYTES);
 #pragma unroll
     for (int part = 0; part < NOPS; ++part) {
-      const int c = part * 3 * D + h * DH;  // q | k | v column blocks, lo plane 3 D further
+      const int c = part * 3 * D + hc;  // q | k | v column blocks, lo plane 3 D further
       ptx::tma_load_2d(sQ(0, part), &tm_q, full_bar, c, row0);
       ptx::tma_load_2d(sK(part), &tm_kv, full_bar, c + D, row0);
     }
 #pragma unroll
-    for (int part = 0; part < NOPS; ++part) {
-      const int c = part * 3 * D + h * DH;
-      ptx::tma_load_2d(sV(part), &tm_kv, full_bar1, c + 2 * D, row0);
-      ptx::tma_load_2d(sQ(1, part), &tm_q, full_bar1, c, row0 + 128);  // rows 192.. belong to the next image (or are zero-filled): never stored
-    }
-  }
+    for (int part = 0; part < NOPS; ++part)  // rows 192.. belong to the next image (or are zero-filled): never stored
+      ptx::tma_load_2d(sQ(1, part), &tm_q, full_bar, part * 3 * D + hc, row0 + 128);
+  };
+  auto load_v = [&](int unit) {  // thread 0
+    const int row0 = (unit / heads) * kNTok, hc = (unit % heads) * DH;
+    ptx::mbar_arrive_expect_tx(full_bar1, Cfg::LOAD_V_BYTES);
+#pragma unroll
+    for (int part = 0; part < NOPS; ++part) ptx::tma_load_2d(sV(part), &tm_kv, full_bar1, part * 3 * D + hc + 2 * D, row0);
+  };
 
   constexpr uint32_t idesc_s = ptx::make_idesc_f16(BF16, 128, kNTok);
   constexpr uint32_t idesc_o = ptx::make_idesc_f16(BF16, 128, DH) | (1u << 16);  // B (= V, keys x d_h) is MN-major
@@ -217,8 +237,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     ptx::umma_commit(s_bar);
   };
-  auto issue_o = [&]() {  // thread 0: O = P V, P read from TMEM
-    ptx::mbar_wait(full_bar1, 0);  // V (and Q tile 1) have landed
+  auto issue_o = [&](uint32_t v_parity) {  // thread 0: O = P V, P read from TMEM
+    ptx::mbar_wait(full_bar1, v_parity);  // V has landed
     ptx::tcgen05_fence_after();
     const uint32_t vh = ptx::kmajor_desc_lo(ptx::smem_u32(sV(0)));
     const uint32_t vl = vh + (Cfg::KV_BYTES >> 4);
@@ -237,7 +257,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::umma_commit(o_bar);
   };
 
+  int unit = blockIdx.x;  // the first unit is static, later ones come from the counter (grid <= units)
   if (threadIdx.x == 0) {
+    load_qk(unit);
+    load_v(unit);
     ptx::mbar_wait(full_bar, 0);
     issue_s(0);
   }
@@ -252,10 +275,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   constexpr int PCH = 32;  // P of a 32-key chunk overwrites that chunk's own S columns (no thread reads another's)
 
 #pragma unroll 1
+  for (uint32_t it = 0; unit < units; ++it) {
+  const int b = unit / heads, h = unit % heads;
+  int next = units;  // thread 0 only
+  if (threadIdx.x == 0) next = (int)(gridDim.x + atomicAdd(sched, 1u));  // latency hides behind the first softmax
+#pragma unroll 1
   for (int tile = 0; tile < 2; ++tile) {
     const bool active = tile == 0 || q < 2;  // tile 1: only rows 128..191 are real
-    mbar_wait_relaxed(s_bar, tile);
+    mbar_wait_relaxed(s_bar, tile);  // two S per unit: the barrier's phase parity is the tile index
     ptx::tcgen05_fence_after();
+    if (threadIdx.x == 0 && tile == 1) {  // both S of this unit are done: its Q and K tiles are free
+      *next_box = next;
+      if (next < units) load_qk(next);
+    }
     float mx = -INFINITY;
     if (active) {
 #pragma unroll 1
@@ -302,10 +334,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
     ptx::tcgen05_fence_before();
     __syncthreads();  // P of all rows is in TMEM, the row-sum halves in shared memory
-    if (threadIdx.x == 0) issue_o();
+    if (threadIdx.x == 0) issue_o(it & 1);
     mbar_wait_relaxed(o_bar, tile);
     ptx::tcgen05_fence_after();
-    if (threadIdx.x == 0 && tile == 0) issue_s(1);  // overlaps the read-out of O below (disjoint columns)
+    if (threadIdx.x == 0) {  // the next S overlaps the read-out of O below (disjoint columns)
+      if (tile == 0) {
+        issue_s(1);
+      } else if (next < units) {  // both P V of this unit are done: V is free, and so are the S / P columns
+        load_v(next);
+        ptx::mbar_wait(full_bar, (it + 1) & 1);
+        issue_s(0);
+      }
+    }
     if (active) {
       // FP16X3: O carries 64 (P) * 64 (V) and the row sum carries 64, so O / l is already in operand units
       const float inv = 1.0f / (x_sum[row] + x_sum[128 + row]);
@@ -331,6 +371,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::tcgen05_fence_before();
     __syncthreads();  // O has been read: the next tile's P V may overwrite it (and the exchange arrays are free)
   }
+  unit = *next_box;  // written before this unit's tile-1 barriers
+  }
+  if (threadIdx.x == 0) {  // the last CTA to finish re-arms the counter for the next launch that uses this slot
+    __threadfence();
+    if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -352,8 +402,16 @@ int launch_tc(const void* qkv_op, int batch, int heads, void* out_op, cudaStream
   if (rc) return rc;
   rc = make_operand_map(&tkv, qkv_op, rows, row_elems, kNTok, DH, BF16);
   if (rc) return rc;
-  PP_CHECK_CUDA(launch_pdl(kern, dim3(batch * heads), dim3(kTcThreads), Cfg::SMEM_BYTES, st, tq, tkv, heads,
-                           reinterpret_cast<uint16_t*>(out_op)));
+  // unit counters: [next unit - grid, finished CTAs], re-armed by the launch's last CTA; consecutive launches rotate
+  // over the slots so that launches overlapping on different streams do not share one
+  static std::atomic<unsigned> slot{0};
+  unsigned* sched = nullptr;
+  PP_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched), g_att_sched));
+  sched += 2 * (slot.fetch_add(1) % kSchedSlots);
+  const int units = batch * heads;
+  const int resident = (DH == 32 ? 2 : 1) * num_sms_att();
+  PP_CHECK_CUDA(launch_pdl(kern, dim3(units < resident ? units : resident), dim3(kTcThreads), Cfg::SMEM_BYTES, st, tq, tkv,
+                           heads, units, sched, reinterpret_cast<uint16_t*>(out_op)));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;
