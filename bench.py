@@ -378,7 +378,7 @@ def main():
                                               share_of_step=dec["ms"] / prof_steps / step_ms_prof)),
             kernel_ms_per_step={k: prof[k]["ms"] / prof_steps for k in ("gemm", "attention", "decode", "other")},
         )
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only: the other ranks would idle in the barrier
             r = cpu_reference(32, 1, 1, flip)
             line["cpu_baseline"] = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
         print(json.dumps(line), flush=True)

@@ -126,16 +126,22 @@ typedef struct pp_gemm_args {
   int32_t res_mod;        /* > 0: the residual has res_mod rows and output row r adds row
                              r % res_mod (pos_embed broadcast over the batch); 0 = (M, ldd)  */
   /* Implicit-GEMM convolution ("taps"), no im2col copy.  With a_taps > 1 the A operand has
-   * logical width k / a_taps and its rows enumerate a ZERO-PADDED NHWC map (b, in_h + 2, in_w + 2);
-   * K-group t is that operand read at row offset a_tap_shift[t] = dy * (in_w + 2) + dx (rows outside
-   * the operand read as zero), so A.W^T is a 3x3 convolution / one ConvTranspose2d sub-pixel phase
-   * evaluated at every padded position.  in_pad = 1 then drops the border rows and maps interior
-   * row (b, i + 1, j + 1) to output row (b, i, j) (or through the up_* scatter).  out_pad = 1
-   * writes into an output map that itself carries a one-pixel border (left untouched: the
-   * caller zeroes it once), ready to be the tap operand of the next layer.                    */
+   * logical width k / a_taps and its rows enumerate a ZERO-PADDED NHWC map; K-group t is that
+   * operand read at row offset a_tap_shift[t] = dy * pitch + dx (rows outside the operand read
+   * as zero), so A.W^T is a 3x3 convolution / one ConvTranspose2d sub-pixel phase evaluated at
+   * every padded position.  in_pad selects the padding layout, drops the border rows and maps
+   * the interior rows to output row (b, i, j) (or through the up_* scatter):
+   *   1  full border:   (in_h + 2) x (in_w + 2) per image, pixel (i, j) at (i + 1, j + 1), pitch in_w + 2
+   *   2  shared border: (in_h + 1) x (in_w + 1) per image, pixel (i, j) at (i + 1, j), pitch in_w + 1;
+   *      row 0 of every image block is zero (top border of this image = bottom border of the one
+   *      before; past the last block the operand reads as zero) and column in_w is zero (right
+   *      border = left border of the next row).  15 % extra rows instead of 31 % on a 16 x 12 map:
+   *      what pp_engine uses.
+   * out_pad (same values) writes into an output map that itself carries such a border (left
+   * untouched: the caller zeroes it once), ready to be the tap operand of the next layer.       */
   int32_t a_taps;         /* 0 / 1 = plain operand                                          */
   int32_t a_tap_shift[9];
-  int32_t in_pad, in_h, in_w; /* in_h / in_w also required by up_* when in_pad = 1           */
+  int32_t in_pad, in_h, in_w; /* in_h / in_w also required by up_* when in_pad != 0          */
   int32_t out_pad;
   int32_t cta_pair;       /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pairs (tcgen05
                              cta_group::2, 256-row tiles) - tuning / tests                   */

@@ -204,9 +204,9 @@ static size_t plan(pp_engine* e) {
     e->qkv = b.take((size_t)M * 3 * D * sizeof(float));
     e->h_op = b.take(pp_operand_bytes(prec, M, FF));
   }
-  // feat_op and d1_op are zero-bordered maps (gh + 2) x (gw + 2) / (2 gh + 2) x (2 gw + 2): the tap
+  // feat_op and d1_op are shared-border maps (gh + 1) x (gw + 1) / (2 gh + 1) x (2 gw + 1) (epilogue.cuh pad_geom mode 2): the tap
   // operands of the head's implicit-GEMM deconvolutions / 3x3 convolution (borders zeroed in finalize)
-  const int64_t Mp0 = (int64_t)e->max_b2 * (e->gh + 2) * (e->gw + 2), Mp1 = (int64_t)e->max_b2 * (2 * e->gh + 2) * (2 * e->gw + 2);
+  const int64_t Mp0 = (int64_t)e->max_b2 * (e->gh + 1) * (e->gw + 1), Mp1 = (int64_t)e->max_b2 * (2 * e->gh + 1) * (2 * e->gw + 1);
   e->feat_op = b.take(pp_operand_bytes(prec, Mp0, D));
   e->feat_bytes = pp_operand_bytes(prec, Mp0, D);
   e->feat_f32 = b.take((size_t)M * D * sizeof(float));
@@ -373,7 +373,7 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
   // Implicit GEMM: the A operand is the zero-bordered input map itself, read at 4 row shifts (taps).
   for (int i = 0; i < 2; ++i) {
     const int cin = i == 0 ? D : DC, h = e->gh << i, w = e->gw << i;
-    const int64_t rows = (int64_t)n_img * (h + 2) * (w + 2);
+    const int64_t rows = (int64_t)n_img * (h + 1) * (w + 1);
     const void* src = i == 0 ? e->at<>(e->feat_op) : e->at<>(e->d1_op);
     void* dst = i == 0 ? e->at<>(e->d1_op) : e->at<>(e->d2_op);
     for (int ph = 0; ph < 4; ++ph) {
@@ -384,11 +384,11 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
         int dy, dx, kk;
         deconv_tap(py, t >> 1, &dy, &kk);
         deconv_tap(px, t & 1, &dx, &kk);
-        g.a_tap_shift[t] = dy * (w + 2) + dx;
+        g.a_tap_shift[t] = dy * (w + 1) + dx;
       }
       g.scale = e->at<float>(e->dc_scale[i]); g.shift = e->at<float>(e->dc_shift[i]); g.act = PP_ACT_RELU;
       g.out_kind = PP_OUT_OPERAND; g.ldd = DC; g.d = dst;
-      g.in_pad = 1; g.in_h = h; g.in_w = w; g.out_pad = i == 0 ? 1 : 0;
+      g.in_pad = 2; g.in_h = h; g.in_w = w; g.out_pad = i == 0 ? 2 : 0;
       g.up_hin = h; g.up_win = w; g.up_py = py; g.up_px = px;
       if (e->profiling) e->prof_gemm_flops -= 2.0 * (rows - (double)n_img * h * w) * DC * 4 * cin;  // border rows are not algorithmic work
       PP_TRY(gemm(e, g, st));
@@ -403,11 +403,11 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
   // --- four scalar branches; the first conv of all four shares its input -> one GEMM, N = 4 D,
   // 9 taps over the zero-bordered feature map ---
   {
-    const int64_t rows = (int64_t)n_img * (e->gh + 2) * (e->gw + 2);
+    const int64_t rows = (int64_t)n_img * (e->gh + 1) * (e->gw + 1);
     pp_gemm_args g = gemm_args(e, rows, 4 * D, 9 * D, e->at<>(e->feat_op), e->at<>(e->w_c1));
     g.a_taps = 9;
-    for (int t = 0; t < 9; ++t) g.a_tap_shift[t] = (t / 3 - 1) * (e->gw + 2) + (t % 3 - 1);
-    g.in_pad = 1; g.in_h = e->gh; g.in_w = e->gw;
+    for (int t = 0; t < 9; ++t) g.a_tap_shift[t] = (t / 3 - 1) * (e->gw + 1) + (t % 3 - 1);
+    g.in_pad = 2; g.in_h = e->gh; g.in_w = e->gw;
     g.scale = e->at<float>(e->c_scale[0]); g.shift = e->at<float>(e->c_shift[0]); g.d = e->at<>(e->c_f32);
     if (e->profiling) e->prof_gemm_flops -= 2.0 * (rows - (double)M) * 4 * D * 9 * D;
     PP_TRY(gemm(e, g, st));

@@ -20,7 +20,8 @@ struct PatchifyParams {
 int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t st);
 
 // Row LayerNorm of fp32 (rows, d) -> operand (rows, d) and, optionally, fp32 (rows, d).
-// pad_gw > 0: operand rows go to the interior of a zero-bordered (pad_gh + 2) x (pad_gw + 2) map per image.
+// pad_gw > 0: operand rows go to the interior of a shared-border (pad_gh + 1) x (pad_gw + 1) map per image
+// (epilogue.cuh pad_geom mode 2).
 int launch_layernorm(int prec, const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
                      void* out_op, float* out_f32, cudaStream_t st, int pad_gh = 0, int pad_gw = 0);
 

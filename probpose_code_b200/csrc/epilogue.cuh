@@ -25,31 +25,48 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Border geometry of a padded map.  mode 1: a one-pixel zero border on every side, (h + 2) x (w + 2) per image,
+// pixel (i, j) at (i + 1, j + 1).  mode 2 ("shared border"): (h + 1) x (w + 1) per image - row 0 of every image
+// block is zero (top border, and bottom border of the image before; rows past the last block read as zero through
+// the TMA out-of-bounds fill) and column w is zero (right border, and left border of the next row: (r, -1) is the
+// same element as (r - 1, w)); pixel (i, j) at (i + 1, j).  15 % extra rows instead of 31 % for a 16 x 12 map.
+struct PadGeom {
+  int xo, yo, ex;  // interior origin, extra rows / columns per image
+};
+__host__ __device__ __forceinline__ PadGeom pad_geom(int mode) {
+  PadGeom g;
+  g.xo = mode == 1 ? 1 : 0;
+  g.yo = mode != 0 ? 1 : 0;
+  g.ex = mode == 1 ? 2 : (mode == 2 ? 1 : 0);
+  return g;
+}
+
 // Logical GEMM row -> output row and validity.
-//   in_pad : the A rows enumerate a zero-padded (in_h + 2) x (in_w + 2) map; border rows produce nothing
+//   in_pad : the A rows enumerate a zero-padded map (pad_geom); border rows produce nothing
 //   up     : stride-2 ConvTranspose2d phase scatter (i, j) -> (2 i + py, 2 j + px)
-//   out_pad: the output map carries a one-pixel zero border of its own (it feeds the next tap GEMM)
+//   out_pad: the output map carries a zero border of its own (it feeds the next tap GEMM)
 __device__ __forceinline__ int64_t map_out_row(const EpiParams& e, int m, bool& valid) {
   valid = m < e.m;
   if (e.up_hin == 0 && e.in_pad == 0 && e.out_pad == 0) return m;
   int b, i, j;
   if (e.in_pad) {
-    const int wp = e.in_w + 2, hp = e.in_h + 2;
+    const PadGeom ig = pad_geom(e.in_pad);
+    const int wp = e.in_w + ig.ex, hp = e.in_h + ig.ex;
     const int jp = m % wp, t = m / wp;
     const int ip = t % hp;
     b = t / hp;
-    valid = valid && jp >= 1 && jp <= e.in_w && ip >= 1 && ip <= e.in_h;
-    i = ip - 1; j = jp - 1;
+    valid = valid && jp >= ig.xo && jp < e.in_w + ig.xo && ip >= ig.yo && ip < e.in_h + ig.yo;
+    i = ip - ig.yo; j = jp - ig.xo;
   } else {
     j = m % e.in_w;
     const int t = m / e.in_w;
     i = t % e.in_h;
     b = t / e.in_h;
   }
-  const int op = e.out_pad;
+  const PadGeom og = pad_geom(e.out_pad);
   if (e.up_hin)
-    return (int64_t)(b * (2 * e.in_h + 2 * op) + 2 * i + e.up_py + op) * (2 * e.in_w + 2 * op) + 2 * j + e.up_px + op;
-  return (int64_t)(b * (e.in_h + 2 * op) + i + op) * (e.in_w + 2 * op) + j + op;
+    return (int64_t)(b * (2 * e.in_h + og.ex) + 2 * i + e.up_py + og.yo) * (2 * e.in_w + og.ex) + 2 * j + e.up_px + og.xo;
+  return (int64_t)(b * (e.in_h + og.ex) + i + og.yo) * (e.in_w + og.ex) + j + og.xo;
 }
 
 // Finish and store NC consecutive columns [n0, n0 + NC) of logical row m (m < e.m checked by

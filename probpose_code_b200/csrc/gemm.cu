@@ -130,6 +130,8 @@ extern "C" int pp_gemm(const pp_gemm_args* a, void* stream) {
   PP_REQUIRE(a->res_mod == 0 || (!a->up_hin && !a->in_pad && !a->out_pad), PP_ERR_INVALID,
              "pp_gemm: res_mod needs the identity row mapping");
   PP_REQUIRE(a->a_taps >= 0 && a->a_taps <= 9, PP_ERR_INVALID, "pp_gemm: a_taps=%d outside [0, 9]", a->a_taps);
+  PP_REQUIRE(a->in_pad >= 0 && a->in_pad <= 2 && a->out_pad >= 0 && a->out_pad <= 2, PP_ERR_INVALID,
+             "pp_gemm: in_pad=%d / out_pad=%d outside {0, 1, 2}", a->in_pad, a->out_pad);
   PP_REQUIRE((!a->in_pad && !(a->out_pad && !a->up_hin)) || (a->in_h > 0 && a->in_w > 0), PP_ERR_INVALID,
              "pp_gemm: in_pad / out_pad need in_h, in_w > 0");
   PP_REQUIRE(!a->up_hin || a->up_win > 0, PP_ERR_INVALID, "pp_gemm: up_hin without up_win");

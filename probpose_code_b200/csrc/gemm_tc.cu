@@ -339,16 +339,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             while (e.res_mod > 0 && rm >= e.res_mod) rm -= e.res_mod;
           }
         } else {
-          const int pad = e.in_pad, op = e.out_pad;
-          const int wp = e.in_w + 2 * pad, hp = e.in_h + 2 * pad;
+          const PadGeom ig = pad_geom(e.in_pad), og = pad_geom(e.out_pad);
+          const int wp = e.in_w + ig.ex, hp = e.in_h + ig.ex;
           int pj = m_first % wp, t = m_first / wp;
           int pi = t % hp, pb = t / hp;
-          const int ow = (e.up_hin ? 2 : 1) * e.in_w + 2 * op, oh = (e.up_hin ? 2 : 1) * e.in_h + 2 * op;
+          const int ow = (e.up_hin ? 2 : 1) * e.in_w + og.ex, oh = (e.up_hin ? 2 : 1) * e.in_h + og.ex;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const bool ok = (m_first + 4 * i < e.m) && pj >= pad && pj < e.in_w + pad && pi >= pad && pi < e.in_h + pad;
-            const int ii = pi - pad, jj = pj - pad;
-            const int oy = e.up_hin ? 2 * ii + e.up_py + op : ii + op, ox = e.up_hin ? 2 * jj + e.up_px + op : jj + op;
+            const bool ok = (m_first + 4 * i < e.m) && pj >= ig.xo && pj < e.in_w + ig.xo && pi >= ig.yo && pi < e.in_h + ig.yo;
+            const int ii = pi - ig.yo, jj = pj - ig.xo;
+            const int oy = e.up_hin ? 2 * ii + e.up_py + og.yo : ii + og.yo, ox = e.up_hin ? 2 * jj + e.up_px + og.xo : jj + og.xo;
             const int64_t orow = (int64_t)(pb * oh + oy) * ow + ox;
             doff[i] = ok ? orow * e.ldd : -1;
             roff[i] = orow * e.ldd;

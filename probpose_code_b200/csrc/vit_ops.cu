@@ -63,13 +63,13 @@ int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t 
 // ---- LayerNorm ----------------------------------------------------------------------------
 // One warp per row; the row lives in registers (NV float4 per lane, d = 128 * NV).
 // Two-pass mean / variance in fp32 like ATen's CPU and CUDA kernels.
-// pad_gw > 0: the operand output is a zero-bordered (pad_gh + 2) x (pad_gw + 2) map per image (the tap
-// operand of the head's implicit-GEMM convolutions); token (y, x) lands at (y + 1, x + 1).
+// pad_gw > 0: the operand output is a shared-border (pad_gh + 1) x (pad_gw + 1) map per image (epilogue.cuh pad_geom
+// mode 2: the tap operand of the head's implicit-GEMM convolutions); token (y, x) lands at (y + 1, x).
 __device__ __forceinline__ int64_t padded_row(int64_t row, int gh, int gw) {
   const int tokens = gh * gw;
   const int64_t b = row / tokens;
   const int t = (int)(row % tokens);
-  return (b * (gh + 2) + t / gw + 1) * (gw + 2) + t % gw + 1;
+  return (b * (gh + 1) + t / gw + 1) * (gw + 1) + t % gw;
 }
 
 template <int PREC, int NV>

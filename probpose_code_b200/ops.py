@@ -113,13 +113,14 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
          residual: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE, out_kind: int = _lib.OUT_F32,
          out: Optional[torch.Tensor] = None, ldd: Optional[int] = None, plane: int = 0, up=None, tile_n: int = 0,
          res_mod: int = 0, taps: Optional[Sequence[int]] = None, in_pad=None, out_pad: bool = False,
-         out_rows: Optional[int] = None, cta_pair: int = 0):
+         out_rows: Optional[int] = None, cta_pair: int = 0, shared_border: bool = False):
     """``pp_gemm``: D = epilogue(A . W^T).  ``a_op`` / ``w_op`` are operand buffers from
     :func:`to_operand`.  Returns the output tensor (fp32, or a uint8 operand buffer).
 
     ``taps``: row shifts of the implicit-GEMM A operand (logical width ``k / len(taps)``);
     ``in_pad=(h, w)``: the A rows enumerate a zero-padded ``(h + 2, w + 2)`` map; ``out_pad``:
-    the output map carries a border too; ``out_rows``: rows of a freshly allocated output."""
+    the output map carries a border too; ``shared_border``: both use the ``(h + 1, w + 1)`` layout (``in_pad`` /
+    ``out_pad`` = 2 in the C ABI) instead; ``out_rows``: rows of a freshly allocated output."""
     dev = a_op.device
     if out_kind == _lib.OUT_F32:
         ldd = n if ldd is None else ldd
@@ -142,7 +143,8 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
     ih, iw = in_pad if in_pad is not None else (0, 0)
     args = _lib.GemmArgs(precision, m, n, k, a_op.data_ptr(), w_op.data_ptr(), _ptr(scale), _ptr(shift),
                          _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n, res_mod,
-                         ntaps, shifts, int(in_pad is not None), ih, iw, int(out_pad), int(cta_pair))
+                         ntaps, shifts, int(in_pad is not None) * (2 if shared_border else 1), ih, iw,
+                         int(bool(out_pad)) * (2 if shared_border else 1), int(cta_pair))
     with torch.cuda.device(dev):
         check(lib().pp_gemm(C.byref(args), _stream()), "pp_gemm")
     return out

@@ -111,16 +111,22 @@ def test_argument_validation_needs_no_launch():
         ops.gemm(ops.to_operand(a, _lib.PREC_BF16), ops.to_operand(a, _lib.PREC_BF16), 128, 128, 100, _lib.PREC_BF16)
 
 
-def _padded_rows(x_nhwc):
-    """(B, h, w, c) -> zero-padded (B * (h + 2) * (w + 2), c) rows, the tap-GEMM A operand."""
+def _padded_rows(x_nhwc, shared=False):
+    """(B, h, w, c) -> zero-padded rows, the tap-GEMM A operand: (B * (h + 2) * (w + 2), c) with a full border, or the
+    shared-border layout (B * (h + 1) * (w + 1), c): zero row on top of every image, zero column on the right."""
     b, h, w, c = x_nhwc.shape
-    p = torch.zeros(b, h + 2, w + 2, c, device=x_nhwc.device)
-    p[:, 1:-1, 1:-1] = x_nhwc
+    if shared:
+        p = torch.zeros(b, h + 1, w + 1, c, device=x_nhwc.device)
+        p[:, 1:, :w] = x_nhwc
+    else:
+        p = torch.zeros(b, h + 2, w + 2, c, device=x_nhwc.device)
+        p[:, 1:-1, 1:-1] = x_nhwc
     return p.reshape(-1, c).contiguous()
 
 
+@pytest.mark.parametrize("shared", [False, True])
 @pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_BF16, _lib.PREC_FP32_SIMT])
-def test_tap_gemm_is_a_3x3_convolution(prec):
+def test_tap_gemm_is_a_3x3_convolution(prec, shared):
     """Implicit GEMM: 9 row-shifted reads of the padded map == Conv2d(3x3, padding=1), no im2col copy."""
     ops = _ops()
     b, h, w, cin, cout = 3, 16, 12, 128, 192
@@ -128,20 +134,22 @@ def test_tap_gemm_is_a_3x3_convolution(prec):
     x = torch.randn(b, h, w, cin, device="cuda", generator=g)
     wt = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05
     bias = torch.randn(cout, device="cuda", generator=g)
-    a = _padded_rows(x)
+    a = _padded_rows(x, shared)
     m = a.shape[0]
+    pitch = w + 1 if shared else w + 2
     wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()  # column (ky*3+kx)*cin + ci
-    taps = [(t // 3 - 1) * (w + 2) + (t % 3 - 1) for t in range(9)]
+    taps = [(t // 3 - 1) * pitch + (t % 3 - 1) for t in range(9)]
     out = ops.gemm(ops.to_operand(a, prec), ops.to_operand(wp, prec), m, cout, 9 * cin, prec, shift=bias,
-                   taps=taps, in_pad=(h, w), out_rows=b * h * w)
+                   taps=taps, in_pad=(h, w), out_rows=b * h * w, shared_border=shared)
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double(), padding=1)
     ref = ref.permute(0, 2, 3, 1).reshape(b * h * w, cout)
     assert _rel(out, ref) <= TOL[prec] * 4
 
 
 @pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_FP32_SIMT])
+@pytest.mark.parametrize("shared", [False, True])
 @pytest.mark.parametrize("out_pad", [False, True])
-def test_tap_gemm_deconv_phases(prec, out_pad):
+def test_tap_gemm_deconv_phases(prec, out_pad, shared):
     """Four sub-pixel phase GEMMs (2x2 taps each) == ConvTranspose2d(k4, s2, p1); with out_pad the
     result lands inside a bordered map whose border stays zero (ready for the next tap GEMM)."""
     ops = _ops()
@@ -149,10 +157,12 @@ def test_tap_gemm_deconv_phases(prec, out_pad):
     g = torch.Generator(device="cuda").manual_seed(9)
     x = torch.randn(b, h, w, cin, device="cuda", generator=g)
     wt = torch.randn(cin, cout, 4, 4, device="cuda", generator=g) * 0.05
-    a = ops.to_operand(_padded_rows(x), prec)
-    m = b * (h + 2) * (w + 2)
+    a = ops.to_operand(_padded_rows(x, shared), prec)
+    pitch = w + 1 if shared else w + 2
+    m = b * (h + 1) * (w + 1) if shared else b * (h + 2) * (w + 2)
     op = int(out_pad)
-    H2, W2 = 2 * h + 2 * op, 2 * w + 2 * op
+    ex = op * (1 if shared else 2)  # extra rows / columns of the output map
+    H2, W2 = 2 * h + ex, 2 * w + ex
     full = torch.zeros(b * H2 * W2, cout, device="cuda")
 
     def tap(phase, t):  # (shift d, kernel index k) of tap t for output parity `phase`
@@ -165,16 +175,18 @@ def test_tap_gemm_deconv_phases(prec, out_pad):
                 dy, ky = tap(py, t >> 1)
                 dx, kx = tap(px, t & 1)
                 cols.append(wt[:, :, ky, kx].t())  # (cout, cin)
-                shifts.append(dy * (w + 2) + dx)
+                shifts.append(dy * pitch + dx)
             wp = torch.cat(cols, dim=1).contiguous()
             ops.gemm(a, ops.to_operand(wp, prec), m, cout, 4 * cin, prec, act=_lib.ACT_RELU, out=full,
-                     up=(h, w, py, px), taps=shifts, in_pad=(h, w), out_pad=out_pad)
+                     up=(h, w, py, px), taps=shifts, in_pad=(h, w), out_pad=out_pad, shared_border=shared)
     ref = torch.relu(torch.nn.functional.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wt.double(), stride=2, padding=1))
     ref = ref.permute(0, 2, 3, 1)
     v = full.view(b, H2, W2, cout)
-    inner = v[:, op:H2 - op, op:W2 - op]
+    inner = v[:, op:, :2 * w] if shared else v[:, op:H2 - op, op:W2 - op]
     assert _rel(inner, ref) <= TOL[prec] * 4
-    if out_pad:
+    if out_pad and shared:
+        assert v[:, 0].abs().max() == 0 and v[:, :, -1].abs().max() == 0
+    elif out_pad:
         assert v[:, 0].abs().max() == 0 and v[:, -1].abs().max() == 0 and v[:, :, 0].abs().max() == 0 and v[:, :, -1].abs().max() == 0
 
 
