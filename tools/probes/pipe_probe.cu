@@ -22,14 +22,14 @@ __global__ void __launch_bounds__(1024) probe(float* out, long long* cyc, float 
     for (int i = 0; i < CH; ++i) {
       if (OP == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
       if (OP == 1) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
-      if (OP == 2) asm volatile("cvt.rn.f16x2.f32 %0, %1, %1;" : "+r"(u[i]) : "f"(v[i]));
-      if (OP == 3) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(v[i]) : "r"(u[i]));
+      if (OP == 2) asm volatile("{.reg .b32 t; cvt.rn.f16x2.f32 t, %0, %0; and.b32 %0, t, 0x3fff3fff;}" : "+f"(v[i]));  // + 1 alu op
+      if (OP == 3) asm volatile("{.reg .f16 lo, hi; .reg .f32 f; mov.b32 {lo, hi}, %0; cvt.f32.f16 f, lo; mov.b32 %0, f;}" : "+r"(u[i]));
       if (OP == 4) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(v[i]));
       if (OP == 5) asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(u[i]) : "r"(u[(i + 1) % CH]));
       if (OP == 6) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(u[i]) : "r"(u[(i + 1) % CH]));
       if (OP == 7) asm volatile("add.f32 %0, %0, %0;" : "+f"(v[i]));
-      if (OP == 8) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %1;" : "+r"(u[i]) : "f"(v[i]));
-      if (OP == 9) asm volatile("{.reg .b32 t; cvt.rn.f16x2.f32 t, %0, %0; mov.b32 %0, t;}" : "+f"(v[i]));  // dependent pack chain
+      if (OP == 8) asm volatile("{.reg .b32 t; cvt.rn.bf16x2.f32 t, %0, %0; and.b32 %0, t, 0x3fff3fff;}" : "+f"(v[i]));
+      if (OP == 9) asm volatile("{.reg .b32 t; and.b32 t, %0, 0x3fff3fff; and.b32 %0, t, 0x3fffffff;}" : "+r"(u[i]));  // 2 alu ops (baseline for the +1 above)
       if (OP == 10) asm volatile("max.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(v[(i + 1) % CH]));
       if (OP == 11) asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) % CH]));
       if (OP == 12) asm volatile("shf.r.wrap.b32 %0, %0, %1, 13;" : "+r"(u[i]) : "r"(u[(i + 1) % CH]));
@@ -67,8 +67,9 @@ int main() {
   cudaMalloc(&cyc, 148 * sizeof(long long));
   run<0>("ex2.approx", out, cyc);
   run<1>("rcp.approx", out, cyc);
-  run<2>("cvt.rn.f16x2.f32 (pack)", out, cyc);
-  run<8>("cvt.rn.bf16x2.f32 (pack)", out, cyc);
+  run<2>("cvt.rn.f16x2.f32 (pack) + and", out, cyc);
+  run<9>("and + and", out, cyc);
+  run<8>("cvt.rn.bf16x2.f32 (pack) + and", out, cyc);
   run<3>("cvt.f32.f16 (unpack)", out, cyc);
   run<4>("fma.f32", out, cyc);
   run<7>("add.f32", out, cyc);
