@@ -181,3 +181,22 @@ def test_graph_replay_is_bit_identical(setup, flip):
     prof = eng.profile_end()
     assert eng.graph_replay_count == n and prof["gemm"]["launches"] > 0
     assert torch.equal(got, plain[2])
+
+
+def test_parity_at_a_batch_that_fills_the_gpu(setup):
+    """BASELINE config 2 shape in miniature: 32 crops with flip-TTA = 64 images = 768 attention units (every persistent
+    attention CTA walks several), 48 GEMM row tiles per CTA pair, decode of 544 maps.  Parity against the oracle on every
+    person, and records bit-identical to the same crops sent in batches of 4 (persons are independent units)."""
+    from probpose_code_b200.engine import Engine
+    n = 32
+    eng = Engine(precision="fp16x3", max_batch=n).load_state_dict(setup["sd"])
+    crops = synth.make_crops(n, seed=77)
+    rec = eng.infer(crops.cuda(), flip_test=True).cpu()
+    ref = setup["ref"].predict(setup["ref"].preprocess(crops), flip_test=True)
+    r = rec.numpy().astype(np.float64)
+    kp = r[..., :2] / [47, 63] * [192, 256]
+    assert np.abs(kp - ref[..., :2]).max() <= KPT_TOL_PX
+    assert np.abs(r[..., 3:] - ref[..., 3:]).max() <= PROB_TOL
+    for lo in range(0, n, 4):
+        part = eng.infer(crops[lo:lo + 4].cuda().contiguous(), flip_test=True).cpu()
+        assert torch.equal(part, rec[lo:lo + 4]), f"records of crops[{lo}:{lo + 4}] depend on the batch composition"
