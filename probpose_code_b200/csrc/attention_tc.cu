@@ -116,6 +116,11 @@ __device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const uint32_t (&r)[
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {  // p 32-byte aligned
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <bool BF16>
@@ -361,11 +366,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if constexpr (SPLIT == 3) split_pair(o[2 * i] * inv, o[2 * i + 1] * inv, hi[i], lo[i]);
           else hi[i] = pack_pair<BF16>(o[2 * i] * inv, o[2 * i + 1] * inv);
         }
-#pragma unroll
-        for (int i = 0; i < 8; i += 4) {
-          *reinterpret_cast<uint4*>(d + c0 + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
-          if constexpr (SPLIT == 3) *reinterpret_cast<uint4*>(d + D + c0 + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
-        }
+        // 16 columns = one 32-byte sector per plane: a single 256-bit store each (sm_100 STG.256) instead of two
+        // 128-bit stores that each leave the lane's sector half written
+        st_global_v8(d + c0, hi);
+        if constexpr (SPLIT == 3) st_global_v8(d + D + c0, lo);
       }
     }
     ptx::tcgen05_fence_before();
@@ -435,6 +439,7 @@ int launch_attention_tc(int prec, const void* qkv_op, int batch, int n, int head
   PP_REQUIRE(attention_mma_supported(n, dh), PP_ERR_UNSUPPORTED,
              "tensor-core attention is built for 192 tokens and head width 32 / 64 (got %d tokens, width %d)", n, dh);
   if (batch == 0) return PP_OK;
+  PP_REQUIRE((reinterpret_cast<uintptr_t>(out_op) & 31) == 0, PP_ERR_INVALID, "attention: out_op %p must be 32-byte aligned", out_op);
   return dh == 32 ? launch_tc_prec<32>(prec, qkv_op, batch, heads, out_op, st)
                   : launch_tc_prec<64>(prec, qkv_op, batch, heads, out_op, st);
 }
