@@ -308,9 +308,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       x_max[hf * 128 + row] = mx;
-    }
-    __syncthreads();
-    if (active) {
+      // the two halves of a row live in warps q and q + 4: only those 64 threads have to meet
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       mx = fmaxf(mx, x_max[(hf ^ 1) * 128 + row]);
       float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains (fixed order: deterministic)
 #pragma unroll 1
