@@ -116,6 +116,23 @@ __device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const uint32_t (&r)[
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// packed fp32 pairs (sm_100: two IEEE fp32 operations per issue slot)
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {  // p 32-byte aligned
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -316,10 +333,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int ch = hf * CHH; ch < (hf + 1) * CHH; ++ch) {
         float v[32];
         ptx::tmem_ld_32x32b_x32(t_s + lane_base + 32 * ch, v);
+        {  // exp2(((s - max) * c) + p) and the four row-sum chains on packed fp32 pairs (FFMA2 / FADD2: two lanes per
+           // issue slot, same operations and order per element as the scalar form; (s - max) first: exact near the maximum)
+          const uint64_t nmx2 = pk2(-mx, -mx), ce2 = pk2(c_exp, c_exp), pe2 = pk2(p_exp, p_exp);
+          uint64_t la = pk2(l4[0], l4[1]), lb = pk2(l4[2], l4[3]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = ex2f(fmaf(v[i] - mx, c_exp, p_exp));  // (s - max) first: exact for scores near the maximum
-          l4[i & 3] += v[i];
+          for (int i = 0; i < 32; i += 2) {
+            float a, b;
+            upk2(fma2(add2(pk2(v[i], v[i + 1]), nmx2), ce2, pe2), a, b);
+            v[i] = ex2f(a);
+            v[i + 1] = ex2f(b);
+            if ((i & 2) == 0) la = add2(la, pk2(v[i], v[i + 1]));
+            else lb = add2(lb, pk2(v[i], v[i + 1]));
+          }
+          upk2(la, l4[0], l4[1]);
+          upk2(lb, l4[2], l4[3]);
         }
         if constexpr (SPLIT == 3) {
           uint32_t r[32];
