@@ -203,10 +203,13 @@ PP_API int pp_revert_heatmaps(const float* heatmaps, const double* warp_mats, in
  * (external package, called from the config's backbone, see SURVEY.md 8c "Backbone").
  *  qkv_op   operand (batch * tokens, 3 * heads * head_dim) in `precision` (the qkv GEMM's
  *           PP_OUT_OPERAND output: [q | k | v] column blocks, heads contiguous inside each)
- *  out_op   operand (batch * tokens, heads * head_dim) out = the proj GEMM's A operand
+ *  out_op   operand (batch * tokens, heads * head_dim) out = the proj GEMM's A operand; 32-byte
+ *           aligned (the tcgen05 kernel writes whole 32-byte sectors with 256-bit stores)
  *  impl     0 = default (tcgen05: S and P.V on the 5th-gen tensor cores, P kept in TMEM),
  *           1 = mma.sync kernel, 2 = tcgen05 kernel (tests compare the two)
- * Built for tokens == 192 and head_dim 32 / 64; tensor-core precisions only.
+ * Built for tokens == 192 and head_dim 32 / 64; tensor-core precisions only.  The tcgen05 kernel runs persistent CTAs
+ * that take (image, head) units from a device-side counter (64 rotating slots, re-armed by each launch's last CTA):
+ * launches may overlap on different streams as long as fewer than 64 of them are in flight at once.
  * ---------------------------------------------------------------------------------- */
 PP_API int pp_attention(int32_t precision, const void* qkv_op, int32_t batch, int32_t tokens, int32_t heads,
                         int32_t head_dim, void* out_op, int32_t impl, void* stream);
