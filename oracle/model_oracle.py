@@ -147,14 +147,53 @@ class ProbMapHeadRef(nn.Module):
         return (self.forward_heatmap(x), self.probability_layers(x), self.visibility_layers(x),
                 self.oks_layers(x), self.error_layers(x))
 
+    @torch.no_grad()
+    def merged(self, feats, feats_flip=None, flip_indices=decode_oracle.COCO_FLIP_INDICES):
+        """``predict`` up to the decode (probmap_head.py:746-774; ``flip_heatmaps`` tta.py:35-39 with
+        flip_mode="heatmap", shift_heatmap=False): merged (heatmaps, prob, vis, oks, err), scalars (B, K)."""
+        out = self.forward(feats)
+        if feats_flip is not None:
+            outf = self.forward(feats_flip)
+            htm = (out[0] + outf[0].flip(-1)[:, flip_indices]) * 0.5
+            scal = [(a + b[:, flip_indices]) * 0.5 for a, b in zip(out[1:], outf[1:])]
+        else:
+            htm, scal = out[0], list(out[1:])
+        return (htm, *[s.flatten(1) for s in scal])
+
+    @torch.no_grad()
+    def predict(self, feats, feats_flip=None, flip_indices=decode_oracle.COCO_FLIP_INDICES, input_size=(192, 256),
+                timings=None):
+        """``ProbMapHead.predict`` (probmap_head.py:715-804) with the ProbMap codec through ``BaseHead.decode``'s
+        per-person loop (base_head.py:64-78).  Returns the record array (B, K, 7) float64
+        [x, y, conf, prob, vis, oks, err/diag] and the merged heatmaps."""
+        import time
+
+        t0 = time.perf_counter()
+        htm, prob, vis, oks, err = self.merged(feats, feats_flip, flip_indices)
+        t1 = time.perf_counter()
+        h, w = htm.shape[-2:]
+        kpts, conf = decode_oracle.decode_instances(htm.numpy(), input_size=input_size, heatmap_size=(w, h))
+        if timings is not None:
+            timings["model_s"] = timings.get("model_s", 0.0) + t1 - t0
+            timings["decode_s"] = time.perf_counter() - t1
+        rec = np.zeros((htm.shape[0], htm.shape[1], 7))
+        rec[..., 0:2] = np.concatenate(kpts, 0)
+        rec[..., 2] = np.concatenate(conf, 0)
+        rec[..., 3] = prob.numpy()
+        rec[..., 4] = vis.numpy()
+        rec[..., 5] = oks.numpy()
+        rec[..., 6] = err.numpy() / np.sqrt(h**2 + w**2)  # probmap_head.py:786-787 (float32 / float64 scalar)
+        return rec, htm
+
+
 
 class ProbPoseRef(nn.Module):
     """TopdownPoseEstimator(backbone=ViT, head=ProbMapHead) restricted to ``predict``."""
 
-    def __init__(self, **vit_kwargs):
+    def __init__(self, head_kwargs=None, **vit_kwargs):
         super().__init__()
         self.backbone = VisionTransformerRef(**vit_kwargs)
-        self.head = ProbMapHeadRef(in_channels=self.backbone.ln1.normalized_shape[0])
+        self.head = ProbMapHeadRef(in_channels=self.backbone.ln1.normalized_shape[0], **(head_kwargs or {}))
 
     @staticmethod
     def preprocess(crops_u8_bgr: torch.Tensor) -> torch.Tensor:
@@ -167,15 +206,11 @@ class ProbPoseRef(nn.Module):
 
     @torch.no_grad()
     def forward_merged(self, inputs, flip_test=True, flip_indices=decode_oracle.COCO_FLIP_INDICES):
-        """Returns merged (heatmaps, prob, vis, oks, err) tensors, err NOT yet /diag."""
-        out = self.head(self.backbone(inputs))
-        if flip_test:
-            outf = self.head(self.backbone(inputs.flip(-1)))
-            htm = (out[0] + outf[0].flip(-1)[:, flip_indices]) * 0.5
-            scal = [(a + b[:, flip_indices]) * 0.5 for a, b in zip(out[1:], outf[1:])]
-        else:
-            htm, scal = out[0], list(out[1:])
-        return (htm, *[s.flatten(1) for s in scal])
+        """Returns merged (heatmaps, prob, vis, oks, err) tensors, err NOT yet /diag
+        (topdown.py:109-112 + probmap_head.py:746-774)."""
+        feats = self.backbone(inputs)
+        feats_flip = self.backbone(inputs.flip(-1)) if flip_test else None
+        return self.head.merged(feats, feats_flip, flip_indices)
 
     @torch.no_grad()
     def predict(self, inputs, flip_test=True, flip_indices=decode_oracle.COCO_FLIP_INDICES, timings=None):
@@ -185,22 +220,11 @@ class ProbPoseRef(nn.Module):
         import time
 
         t0 = time.perf_counter()
-        htm, prob, vis, oks, err = self.forward_merged(inputs, flip_test, flip_indices)
-        t1 = time.perf_counter()
-        h, w = htm.shape[-2:]
-        kpts, conf = decode_oracle.decode_instances(htm.numpy(), heatmap_size=(w, h))
-        t2 = time.perf_counter()
+        feats = self.backbone(inputs)
+        feats_flip = self.backbone(inputs.flip(-1)) if flip_test else None
         if timings is not None:
-            timings["model_s"] = t1 - t0
-            timings["decode_s"] = t2 - t1
-        rec = np.zeros((htm.shape[0], htm.shape[1], 7))
-        rec[..., 0:2] = np.concatenate(kpts, 0)
-        rec[..., 2] = np.concatenate(conf, 0)
-        rec[..., 3] = prob.numpy()
-        rec[..., 4] = vis.numpy()
-        rec[..., 5] = oks.numpy()
-        rec[..., 6] = err.numpy() / math.sqrt(h**2 + w**2)  # probmap_head.py:786-787
-        return rec
+            timings["model_s"] = time.perf_counter() - t0
+        return self.head.predict(feats, feats_flip, flip_indices, timings=timings)[0]
 
 
 class ViTPoseRef(nn.Module):
