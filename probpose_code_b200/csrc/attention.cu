@@ -278,11 +278,8 @@ int launch_mma(const void* qkv_op, int batch, int heads, void* out_op, cudaStrea
   constexpr int NOPS = SPLIT == 3 ? 2 : 1;
   constexpr int SMEM = 2 * NOPS * NTOK * (DH * 2 + 16);
   auto kern = attention_mma_kernel<NTOK, DH, SPLIT, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   PP_CHECK_CUDA(launch_pdl(kern, dim3(batch * heads), dim3(kAttThreads), SMEM, st, reinterpret_cast<const uint16_t*>(qkv_op), heads,
                            reinterpret_cast<uint16_t*>(out_op)));
   count_launch();

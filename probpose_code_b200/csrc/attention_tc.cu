@@ -3,7 +3,9 @@
 // Reference semantics: mmpretrain 1.2.0 MultiheadAttention.forward (see attention.cu) =
 //   softmax(Q K^T * d_h^-0.5) V per (image, head), Q / K / V = column blocks of the qkv GEMM output.
 //
-// PERSISTENT CTAs (8 warps), two per SM, each walking (image, head) units handed out by an atomic counter; the
+// PERSISTENT CTAs (8 warps), two per SM, each walking the (image, head) units blockIdx.x, blockIdx.x + gridDim.x, ...
+// (a static schedule: the units cost the same, and a launch carries no device-global scheduler state, so concurrent
+// launches on other streams and CUDA-graph replays cannot interfere); the
 // next unit's Q / K tiles are requested as soon as the current unit's last S = Q K^T has completed and its V as soon
 // as the last P V has, so every load after the first hides behind the softmax / P V / read-out of the unit before
 // (single-buffered shared memory: 80 KB per CTA), and barrier set-up / TMEM allocation happen once per CTA.
@@ -29,8 +31,6 @@
 
 #include <math.h>
 
-#include <atomic>
-
 namespace pp {
 
 int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t row_elems, int box_rows, int box_cols,
@@ -40,18 +40,8 @@ namespace {
 
 constexpr int kTcThreads = 256;
 constexpr int kNTok = 192;
-constexpr int kSchedSlots = 64;
-__device__ unsigned g_att_sched[2 * kSchedSlots];  // zero-initialised; see launch_tc
 
-int num_sms_att() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-}
+int num_sms_att() { return device_sm_count(); }
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -179,7 +169,7 @@ struct AttCfg {
 template <int DH, int SPLIT, bool BF16>
 __global__ void __launch_bounds__(kTcThreads, DH == 32 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const int heads,
-                    const int units, unsigned* __restrict__ sched, uint16_t* __restrict__ out_op) {
+                    const int units, uint16_t* __restrict__ out_op) {
   using Cfg = AttCfg<DH, SPLIT>;
   constexpr int NOPS = Cfg::NOPS, ROWB = Cfg::ROWB;
   extern __shared__ uint8_t att_raw[];
@@ -189,7 +179,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* s_bar = full_bar + 2;
   uint64_t* o_bar = full_bar + 3;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 4);
-  volatile int* next_box = reinterpret_cast<volatile int*>(full_bar + 6);  // thread 0 -> CTA: the unit after this one
   float* x_max = reinterpret_cast<float*>(smem + Cfg::OFF_X);  // [half][row]
   float* x_sum = x_max + 2 * 128;
 
@@ -279,7 +268,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::umma_commit(o_bar);
   };
 
-  int unit = blockIdx.x;  // the first unit is static, later ones come from the counter (grid <= units)
+  int unit = blockIdx.x;  // static schedule: unit, unit + gridDim.x, ... (grid <= units)
   if (threadIdx.x == 0) {
     load_qk(unit);
     load_v(unit);
@@ -299,17 +288,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll 1
   for (uint32_t it = 0; unit < units; ++it) {
   const int b = unit / heads, h = unit % heads;
-  int next = units;  // thread 0 only
-  if (threadIdx.x == 0) next = (int)(gridDim.x + atomicAdd(sched, 1u));  // latency hides behind the first softmax
+  const int next = unit + (int)gridDim.x;
 #pragma unroll 1
   for (int tile = 0; tile < 2; ++tile) {
     const bool active = tile == 0 || q < 2;  // tile 1: only rows 128..191 are real
     mbar_wait_relaxed(s_bar, tile);  // two S per unit: the barrier's phase parity is the tile index
     ptx::tcgen05_fence_after();
-    if (threadIdx.x == 0 && tile == 1) {  // both S of this unit are done: its Q and K tiles are free
-      *next_box = next;
-      if (next < units) load_qk(next);
-    }
+    if (threadIdx.x == 0 && tile == 1 && next < units) load_qk(next);  // both S of this unit are done: its Q and K tiles are free
     float mx = -INFINITY;
     if (active) {
 #pragma unroll 1
@@ -402,15 +387,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     ptx::tcgen05_fence_before();
     __syncthreads();  // O has been read: the next tile's P V may overwrite it (and the exchange arrays are free)
   }
-  unit = *next_box;  // written before this unit's tile-1 barriers
-  }
-  if (threadIdx.x == 0) {  // the last CTA to finish re-arms the counter for the next launch that uses this slot
-    __threadfence();
-    if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
-      sched[0] = 0;
-      sched[1] = 0;
-      __threadfence();
-    }
+  unit = next;
   }
   if (warp == 1) {
     ptx::tcgen05_fence_after();
@@ -422,27 +399,18 @@ template <int DH, int SPLIT, bool BF16>
 int launch_tc(const void* qkv_op, int batch, int heads, void* out_op, cudaStream_t st) {
   using Cfg = AttCfg<DH, SPLIT>;
   auto kern = attention_tc_kernel<DH, SPLIT, BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int64_t rows = (int64_t)batch * kNTok, row_elems = (int64_t)Cfg::NOPS * 3 * heads * DH;
   CUtensorMap tq, tkv;
   int rc = make_operand_map(&tq, qkv_op, rows, row_elems, 128, DH, BF16);
   if (rc) return rc;
   rc = make_operand_map(&tkv, qkv_op, rows, row_elems, kNTok, DH, BF16);
   if (rc) return rc;
-  // unit counters: [next unit - grid, finished CTAs], re-armed by the launch's last CTA; consecutive launches rotate
-  // over the slots so that launches overlapping on different streams do not share one
-  static std::atomic<unsigned> slot{0};
-  unsigned* sched = nullptr;
-  PP_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched), g_att_sched));
-  sched += 2 * (slot.fetch_add(1) % kSchedSlots);
   const int units = batch * heads;
   const int resident = (DH == 32 ? 2 : 1) * num_sms_att();
   PP_CHECK_CUDA(launch_pdl(kern, dim3(units < resident ? units : resident), dim3(kTcThreads), Cfg::SMEM_BYTES, st, tq, tkv,
-                           heads, units, sched, reinterpret_cast<uint16_t*>(out_op)));
+                           heads, units, reinterpret_cast<uint16_t*>(out_op)));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
   return PP_OK;

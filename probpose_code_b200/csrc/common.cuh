@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <atomic>
 #include <utility>
 
 #include "../../include/probpose_b200.h"
@@ -39,6 +40,19 @@ extern thread_local int64_t g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
 constexpr int kWarp = 32;
+
+// One-time set-up that is PER DEVICE (function attributes such as MaxDynamicSharedMemorySize belong to a device's
+// context; several devices may be driven from one process): first() is true once per CUDA device.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done[4] = {};  // devices 0 .. 255
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const uint64_t bit = 1ull << (dev & 63);
+    return !(done[(dev >> 6) & 3].fetch_or(bit) & bit);
+  }
+};
+int device_sm_count();  // capi.cu: SM count of the CURRENT device (cached per device)
 
 // ---- programmatic dependent launch -------------------------------------------------------
 // Every kernel of the step is launched with programmatic stream serialization: it may start (barrier

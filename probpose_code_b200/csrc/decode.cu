@@ -778,14 +778,13 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
   const int64_t count = (int64_t)batch * cfg->num_keypoints;
   PP_REQUIRE(count < (1ll << 31), PP_ERR_INVALID, "pp_decode: batch too large");
   p.count = (int)count;
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   auto kern = cfg->input_is_logits ? decode_kernel<64, 48, true> : decode_kernel<64, 48, false>;
-  if (!attr_set) {  // shared memory for kDecCtasPerSm CTAs per SM (about 110 KB each)
+  if (attr_set.first()) {  // shared memory for kDecCtasPerSm CTAs per SM (about 110 KB each)
     PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
     PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
     PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
   }
   const int grid = (int)((count + kDecWarps - 1) / kDecWarps);
   PP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDecThreads), sizeof(DecodeSmem), (cudaStream_t)stream, p));

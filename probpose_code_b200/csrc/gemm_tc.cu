@@ -629,25 +629,14 @@ int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t r
   return PP_OK;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
-}
+static int num_sms() { return device_sm_count(); }
 
 template <int BN, int SPLIT, bool BF16, int OUT, int ACCS, bool PAIR>
 static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SPLIT, ACCS, PAIR>;
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   auto kern = gemm_tc_kernel<BN, SPLIT, BF16, OUT, ACCS, PAIR>;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  if (attr_set.first()) PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int nops = SPLIT == 3 ? 2 : 1;
   CUtensorMap tma, tmw;
   int rc = make_operand_map(&tma, a.a, a.m, (int64_t)nops * tp.tap_k, kBM, Cfg::BK, BF16);

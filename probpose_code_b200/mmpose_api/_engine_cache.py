@@ -22,13 +22,16 @@ class EngineCache:
         self.stamp = None
         self.capacity = 0
 
-    def get(self, named_tensors: Dict[str, torch.Tensor], batch: int, device: torch.device) -> Engine:
+    def get(self, named_tensors: Dict[str, torch.Tensor], images: int, device: torch.device) -> Engine:
+        """``images``: how many images the call pushes through the network - batch x passes, i.e. TWICE the
+        batch for a flip_test call.  The engine is rebuilt (next power of two) when a call needs more; the C side
+        admits passes x batch <= 2 x max_batch, so ``capacity`` (in images) is exactly that bound."""
         stamp = (str(device),) + tuple((n, t._version, t.data_ptr()) for n, t in named_tensors.items())
-        if self.engine is None or batch > self.capacity or device != self.engine.device:
-            cap = max(16, 1 << (max(batch, 1) - 1).bit_length())
+        if self.engine is None or images > self.capacity or device != self.engine.device:
+            cap = max(32, 1 << (max(images, 1) - 1).bit_length())
             self.engine = None  # release the old workspace first
-            self.engine = Engine(precision=self.precision, max_batch=cap, device=device, **self.kwargs)
-            self.capacity = 2 * cap  # single-pass calls may use the flip half too
+            self.engine = Engine(precision=self.precision, max_batch=cap // 2, device=device, **self.kwargs)
+            self.capacity = cap
             self.stamp = None
         if stamp != self.stamp:
             self.engine.load_state_dict(named_tensors)

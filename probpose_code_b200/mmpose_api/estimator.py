@@ -85,10 +85,11 @@ class TopdownPoseEstimator(nn.Module):
     # ---- fused engine -----------------------------------------------------------------
     def _fusable(self) -> bool:
         return (isinstance(self.backbone, VisionTransformer) and self.with_head and isinstance(self.head, (ProbMapHead, HeatmapHead))
-                and not self.with_neck and self.head.decoder is not None
+                and not self.with_neck and self.head.decoder is not None and self.head.fused_decoder()
+                and self.head.fused_test_cfg(self.test_cfg)
                 and self.backbone._cache.precision == self.head._cache.precision)
 
-    def _fused_engine(self, batch: int, device):
+    def _fused_engine(self, images: int, device):
         if self._fused is None:
             kw = dict(self.backbone._cache.kwargs)
             hk = self.head._cache.kwargs
@@ -100,7 +101,7 @@ class TopdownPoseEstimator(nn.Module):
             self._fused = EngineCache(kw, self.backbone._cache.precision)
         tensors = dict(self.backbone.engine_tensors())
         tensors.update(self.head.engine_tensors())
-        return self._fused.get(tensors, batch, device)
+        return self._fused.get(tensors, images, device)
 
     def _device(self):
         return self.backbone.pos_embed.device
@@ -167,11 +168,10 @@ class TopdownPoseEstimator(nn.Module):
     def _predict_fused(self, inputs: torch.Tensor, data_samples: list) -> list:
         """One ``pp_engine_infer`` call for the batch (uint8 BGR or normalised fp32 crops)."""
         cfg = self.test_cfg
-        self.head.check_test_cfg(cfg)
         flip = bool(cfg.get("flip_test", False))
         want_hm = bool(cfg.get("output_heatmaps", False))
         flip_indices = data_samples[0].metainfo["flip_indices"] if flip else None
-        eng = self._fused_engine(inputs.shape[0], inputs.device)
+        eng = self._fused_engine(inputs.shape[0] * (2 if flip else 1), inputs.device)
         out = eng.infer(inputs, flip_test=flip, flip_indices=flip_indices, return_heatmaps=want_hm)
         records, heatmaps = out if want_hm else (out, None)
         fields = [PixelData(heatmaps=hm) for hm in heatmaps] if want_hm else None

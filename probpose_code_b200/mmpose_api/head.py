@@ -179,17 +179,55 @@ class ProbMapHead(BaseHead):
                 for i in range(rec.shape[0])]
 
     @staticmethod
-    def check_test_cfg(test_cfg: dict) -> None:
+    def fused_test_cfg(test_cfg: dict) -> bool:
+        """The fused kernels merge the flipped pass as ``flip_mode="heatmap", shift_heatmap=False`` (the shipped
+        test_cfg); other settings run the flip merge as tensor ops (utils.flip_heatmaps) before the decode kernel."""
+        return not test_cfg.get("flip_test", False) or (test_cfg.get("flip_mode", "heatmap") == "heatmap"
+                                                        and not test_cfg.get("shift_heatmap", False))
+
+    def fused_decoder(self) -> bool:
+        """The fused sparsemax / TTA / expected-value kernel implements the ProbMap codec's ``"gaussian"`` decode; with any
+        other ``decoder`` (the constructor default is UDPHeatmap, as in the reference) ``predict`` goes through
+        ``BaseHead.decode`` -> that codec, as probmap_head.py:776 does."""
+        from .codec import ProbMap
+        return isinstance(self.decoder, ProbMap) and self.decoder.heatmap_type == "gaussian"
+
+    def _predict_generic(self, feats, batch_data_samples, test_cfg: dict):
+        """probmap_head.py:746-804 step by step on device tensors (any flip_mode / shift_heatmap / decoder)."""
+        from .utils import flip_heatmaps
         if test_cfg.get("flip_test", False):
-            if test_cfg.get("flip_mode", "heatmap") != "heatmap" or test_cfg.get("shift_heatmap", False):
-                raise NotImplementedError('flip_test is implemented for flip_mode="heatmap", shift_heatmap=False '
-                                          "(the shipped ProbPose test_cfg)")
+            assert isinstance(feats, list) and len(feats) == 2
+            flip_indices = list(batch_data_samples[0].metainfo["flip_indices"])
+            htm, *scal = self.forward(feats[0])
+            htm_f, *scal_f = self.forward(feats[1])
+            htm_f = flip_heatmaps(htm_f, flip_mode=test_cfg.get("flip_mode", "heatmap"), flip_indices=flip_indices,
+                                  shift_heatmap=test_cfg.get("shift_heatmap", False))
+            heatmaps = (htm + htm_f) * 0.5
+            scal = [(a + b[:, flip_indices]) * 0.5 for a, b in zip(scal, scal_f)]
+        else:
+            heatmaps, *scal = self.forward(feats)
+        b, c, h, w = heatmaps.shape
+        preds = self.decode(heatmaps)
+        prob, vis, oks, err = [s.detach().cpu().numpy().reshape((b, 1, c)) for s in scal]
+        err = err / np.sqrt(h**2 + w**2)
+        for pi, p in enumerate(preds):
+            p.set_field(p["keypoint_scores"], "keypoints_conf")
+            p.set_field(prob[pi], "keypoints_probs")
+            p.set_field(vis[pi], "keypoints_visible")
+            p.set_field(oks[pi], "keypoints_oks")
+            p.set_field(err[pi], "keypoints_error")
+            if not self.freeze_oks:
+                p.set_field(oks[pi], "keypoint_scores")
+        if test_cfg.get("output_heatmaps", False):
+            return preds, [PixelData(heatmaps=hm) for hm in heatmaps.detach()]
+        return preds
 
     @torch.no_grad()
     def predict(self, feats, batch_data_samples, test_cfg: dict = {}):
         """probmap_head.py:715-804.  Sparsemax, flip merge, decode and scalar merge run in one
         kernel over both passes' raw outputs."""
-        self.check_test_cfg(test_cfg)
+        if not (self.fused_test_cfg(test_cfg) and self.fused_decoder()):
+            return self._predict_generic(feats, batch_data_samples, test_cfg)
         want_hm = bool(test_cfg.get("output_heatmaps", False))
         if test_cfg.get("flip_test", False):
             assert isinstance(feats, list) and len(feats) == 2
@@ -268,7 +306,11 @@ class HeatmapHead(BaseHead):
         self._named = None
 
     engine_tensors = ProbMapHead.engine_tensors
-    check_test_cfg = staticmethod(ProbMapHead.check_test_cfg)
+    fused_test_cfg = staticmethod(ProbMapHead.fused_test_cfg)
+
+    def fused_decoder(self) -> bool:
+        from .codec import UDPHeatmap
+        return isinstance(self.decoder, UDPHeatmap) and self.decoder.heatmap_type == "gaussian"
 
     @torch.no_grad()
     def forward(self, feats: Tuple[torch.Tensor]) -> torch.Tensor:
@@ -293,7 +335,18 @@ class HeatmapHead(BaseHead):
     @torch.no_grad()
     def predict(self, feats, batch_data_samples, test_cfg: dict = {}):
         """heatmap_head.py:216-265: flip merge + decode in one kernel over both passes' heatmaps."""
-        self.check_test_cfg(test_cfg)
+        if not (self.fused_test_cfg(test_cfg) and self.fused_decoder()):  # any other flip_mode / shift / codec: tensor ops
+            from .utils import flip_heatmaps
+            if test_cfg.get("flip_test", False):
+                assert isinstance(feats, list) and len(feats) == 2
+                hm = (self.forward(feats[0]) + flip_heatmaps(
+                    self.forward(feats[1]), flip_mode=test_cfg.get("flip_mode", "heatmap"),
+                    flip_indices=batch_data_samples[0].metainfo["flip_indices"],
+                    shift_heatmap=test_cfg.get("shift_heatmap", False))) * 0.5
+            else:
+                hm = self.forward(feats)
+            preds = self.decode(hm)
+            return (preds, [PixelData(heatmaps=h) for h in hm.detach()]) if test_cfg.get("output_heatmaps", False) else preds
         want_hm = bool(test_cfg.get("output_heatmaps", False))
         blur = getattr(self.decoder, "blur_kernel_size", 11)
         if test_cfg.get("flip_test", False):

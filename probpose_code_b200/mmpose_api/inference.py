@@ -95,8 +95,11 @@ def inference_topdown(model, img: Union[np.ndarray, torch.Tensor], bboxes: Optio
     from .. import ops
     from . import COCO_FLIP_INDICES
 
-    if isinstance(img, str):
-        raise NotImplementedError("pass the decoded frame: image file loading (LoadImage) is outside the GPU path")
+    if isinstance(img, str):  # LoadImage (mmcv.imfrombytes, cv2 backend, color): BGR uint8 (apis/inference.py:176-183)
+        import cv2
+        path, img = img, cv2.imread(img, cv2.IMREAD_COLOR)
+        if img is None:
+            raise FileNotFoundError(f"cannot read image {path!r}")
     h, w = img.shape[:2]
     if bboxes is None or len(bboxes) == 0:
         bboxes = np.array([[0, 0, w, h]], dtype=np.float32)
@@ -114,7 +117,9 @@ def inference_topdown(model, img: Union[np.ndarray, torch.Tensor], bboxes: Optio
     for bbox in bboxes:
         bbox = np.asarray(bbox)[None, :4]  # shape (1, 4), inference.py:185
         center, scale, m = affine.geometry(bbox)
-        ds = PoseDataSample(metainfo=dict(input_size=(in_w, in_h), input_center=center, input_scale=scale, flip_indices=fi))
+        # ori_shape / img_shape: what LoadImage + PackPoseInputs record (merge_data_samples reads ori_shape)
+        ds = PoseDataSample(metainfo=dict(input_size=(in_w, in_h), input_center=center, input_scale=scale, flip_indices=fi,
+                                          ori_shape=(h, w), img_shape=(h, w)))
         ds.gt_instances = InstanceData(bboxes=bbox, bbox_scores=np.ones(1, dtype=np.float32))
         samples.append(ds)
         mats.append(m)

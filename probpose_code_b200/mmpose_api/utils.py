@@ -60,6 +60,32 @@ def get_warp_matrix(center, scale, rot, output_size, shift=(0.0, 0.0), inv=False
     return _get_affine_transform(dst, src) if inv else _get_affine_transform(src, dst)
 
 
+def flip_heatmaps(heatmaps: torch.Tensor, flip_indices=None, flip_mode: str = "heatmap", shift_heatmap: bool = True):
+    """mmpose/models/utils/tta.py:9-67 on device tensors, every ``flip_mode``.  The fused kernels cover
+    ``flip_mode="heatmap", shift_heatmap=False`` (the shipped test_cfg); any other setting takes this tensor path."""
+    if flip_mode == "heatmap":
+        heatmaps = heatmaps.flip(-1)
+        if flip_indices is not None:
+            assert len(flip_indices) == heatmaps.shape[1]
+            heatmaps = heatmaps[:, list(flip_indices)]
+    elif flip_mode in ("udp_combined", "offset"):
+        group, neg = (3, 1) if flip_mode == "udp_combined" else (2, 0)
+        b, c, h, w = heatmaps.shape
+        heatmaps = heatmaps.reshape(b, c // group, -1, h, w).flip(-1)
+        if flip_indices is not None:
+            assert len(flip_indices) == c // group
+            heatmaps = heatmaps[:, list(flip_indices)]
+        heatmaps = heatmaps.clone()
+        heatmaps[:, :, neg] = -heatmaps[:, :, neg]
+        heatmaps = heatmaps.reshape(b, c, h, w)
+    else:
+        raise ValueError(f'Invalid flip_mode value "{flip_mode}"')
+    if shift_heatmap:
+        heatmaps = heatmaps.clone()
+        heatmaps[..., 1:] = heatmaps[..., :-1].clone()
+    return heatmaps
+
+
 def _as_cuda(heatmap) -> torch.Tensor:
     t = heatmap if torch.is_tensor(heatmap) else torch.from_numpy(np.ascontiguousarray(heatmap, np.float32))
     return t.detach().float().cuda().contiguous() if not t.is_cuda else t.detach().float().contiguous()

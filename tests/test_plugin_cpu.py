@@ -54,8 +54,38 @@ def test_constructor_errors_match_the_reference():
         head.decode(torch.zeros(1, 17, 64, 48))
     with pytest.raises(NotImplementedError):
         head.loss(None, None)
-    with pytest.raises(NotImplementedError):
-        head.check_test_cfg(dict(flip_test=True, flip_mode="udp_combined"))
+    # other flip modes / codecs are not an error: they leave the fused kernels for the tensor path (tta.py:9-67)
+    assert head.fused_test_cfg(dict(flip_test=True, flip_mode="heatmap", shift_heatmap=False))
+    assert not head.fused_test_cfg(dict(flip_test=True, flip_mode="udp_combined"))
+    assert not head.fused_test_cfg(dict(flip_test=True, shift_heatmap=True))
+    assert not head.fused_decoder()
+    default = api.ProbMapHead(in_channels=384, out_channels=17, deconv_out_channels=(256, 256), deconv_kernel_sizes=(4, 4),
+                              normalize=1.0)  # constructor default decoder = UDPHeatmap, as in the reference
+    assert isinstance(default.decoder, api.UDPHeatmap) and not default.fused_decoder()
+
+
+def test_flip_heatmaps_matches_the_reference_semantics():
+    """utils.flip_heatmaps restates mmpose/models/utils/tta.py:9-67 (all modes, shift)."""
+    from probpose_code_b200.mmpose_api.utils import flip_heatmaps
+    g = torch.Generator().manual_seed(0)
+    fi = [0, 2, 1]
+    hm = torch.rand(2, 3, 4, 5, generator=g)
+    out = flip_heatmaps(hm, flip_indices=fi, flip_mode="heatmap", shift_heatmap=False)
+    assert torch.equal(out, hm.flip(-1)[:, fi])
+    sh = flip_heatmaps(hm, flip_indices=fi, flip_mode="heatmap", shift_heatmap=True)
+    assert torch.equal(sh[..., 1:], out[..., :-1]) and torch.equal(sh[..., 0], out[..., 0])
+    comb = torch.rand(2, 9, 4, 5, generator=g)
+    out = flip_heatmaps(comb, flip_indices=fi, flip_mode="udp_combined", shift_heatmap=False)
+    ref = comb.view(2, 3, 3, 4, 5).flip(-1)[:, fi].clone()
+    ref[:, :, 1] = -ref[:, :, 1]
+    assert torch.equal(out, ref.view(2, 9, 4, 5))
+    off = torch.rand(2, 6, 4, 5, generator=g)
+    out = flip_heatmaps(off, flip_indices=fi, flip_mode="offset", shift_heatmap=False)
+    ref = off.view(2, 3, 2, 4, 5).flip(-1)[:, fi].clone()
+    ref[:, :, 0] = -ref[:, :, 0]
+    assert torch.equal(out, ref.view(2, 6, 4, 5))
+    with pytest.raises(ValueError, match="Invalid flip_mode"):
+        flip_heatmaps(hm, flip_mode="nope")
 
 
 def test_no_cpu_fallback():
