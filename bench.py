@@ -264,7 +264,7 @@ def main():
     n_rot = 16
     host = [synth.make_crops(B, seed=1000 * rank + i).pin_memory() for i in range(n_rot)]
     resident = [h.to(dev) for h in host]
-    eng = model._fused_engine(B, dev)
+    eng = model._fused_engine(B * (2 if flip else 1), dev)
     rec = torch.empty((B, 17, 7), dtype=torch.float32, device=dev)
     from probpose_code_b200.sharding import gather_records
     fi = api.COCO_FLIP_INDICES

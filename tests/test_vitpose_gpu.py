@@ -84,8 +84,15 @@ def test_unfused_head_and_codec_api(setup):
     kb, sb = model.head.decoder.batch_decode(hm)
     np.testing.assert_array_equal(kb[0], k_np)
     assert model.head.decoder.support_batch_decoding
-    with pytest.raises(NotImplementedError):
-        model.head.predict(feats, api.make_data_samples(3), test_cfg=dict(flip_test=True, flip_mode="udp_combined"))
+    # shift_heatmap=True (the default of tta.flip_heatmaps) leaves the fused kernel for the tensor path: same result as
+    # merging by hand and decoding the merged maps
+    from probpose_code_b200.mmpose_api.utils import flip_heatmaps
+    feats_f = model.extract_feat(x.flip(-1))
+    cfg = dict(flip_test=True, flip_mode="heatmap", shift_heatmap=True)
+    got = model.head.predict([feats, feats_f], api.make_data_samples(3), test_cfg=cfg)
+    merged = (hm + flip_heatmaps(model.head.forward(feats_f), flip_indices=api.COCO_FLIP_INDICES, shift_heatmap=True)) * 0.5
+    kb2, _ = model.head.decoder.batch_decode(merged)
+    np.testing.assert_array_equal(got[1].keypoints, kb2[1])
     with pytest.raises(ValueError):
         api.MODELS.build(dict(type="HeatmapHead", in_channels=384, out_channels=17, deconv_out_channels=(256, 256), deconv_kernel_sizes=(4,)))
     with pytest.raises(ValueError):

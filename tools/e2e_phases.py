@@ -20,7 +20,7 @@ for i in range(N):
     model.test_step(dict(inputs=host[i % 4], data_samples=samples))
 t_all = (time.perf_counter() - t0) / N
 dev = [h.cuda() for h in host]
-eng = model._fused_engine(B, dev[0].device)
+eng = model._fused_engine(2 * B, dev[0].device)
 rec = torch.empty((B, 17, 7), device="cuda")
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for i in range(N):

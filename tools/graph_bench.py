@@ -29,7 +29,7 @@ def main():
     model = api.MODELS.build(api.probpose_small_cfg(precision="fp16x3", flip_test=True))
     model.load_state_dict(synth.make_state_dict(seed=0))
     model.to(dev)
-    eng = model._fused_engine(64, dev)
+    eng = model._fused_engine(128, dev)
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         for b in [int(x) for x in args.batches.split(",")]:
