@@ -92,10 +92,17 @@ def decode_leg(eng, dev, fi, batch: int = 256, sets: int = 4, iters: int = 40) -
         for i in range(sets):
             run(i)
         torch.cuda.synchronize()
+        # the launches are replayed from ONE CUDA graph: a Python / ctypes call costs ~10 us of host time, more than the
+        # kernel itself, and back-to-back launches issued from the host would measure the host, not the kernel
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(iters):
+                run(i)
+        graph.replay()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(iters):
-            run(i)
+        graph.replay()
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1e3 / iters
