@@ -10,32 +10,24 @@
 // post_processing.py:13-39,308-430 (see include/probpose_b200.h: pp_decode).
 //
 // HBM-bound by design: every map (12 KB, 24 KB with TTA) is read exactly once from HBM; the only
-// global write is the 28-byte record.  PERSISTENT CTAs, one per SM, each owning a contiguous range of maps:
-//   * a PRODUCER warp (one elected thread) walks the range and feeds a kStages-deep ring of 12-KB shared-memory
-//     stages with cp.async.bulk (1-D bulk copies, completion bytes on an mbarrier): the loads never wait for a
-//     dependent chain,
-//   * kConsumers CONSUMER warps claim maps in ring order (shared-memory counter), ONE WARP PER MAP: wait for the
-//     map's stage(s), stream the stage through registers (24 conflict-free 128-bit shared-memory loads per lane,
-//     only the maximum of each float4 is kept), compact the candidates into a short list and hand the stage back
-//     to the producer at once - a stage is held for a few hundred instructions, the long list-only tail of the
-//     decode (threshold, merge, convolution, arg max: ~1 500 latency-bound instructions) holds no stage, which is
-//     what lets 31 warps per SM overlap their tails while 8 stages keep HBM busy,
-//   * max (CREDUX) -> candidate set {z > max - T}: the few float4 that hold a candidate are re-read from the stage
-//     and ballot-compacted into a short list (a trained head leaves 2-3 pixels) -> exact
-//     sparsemax threshold on the list (all-pairs rank / prefix-sum form of Martins & Astudillo Alg. 1 for
-//     <= 32 candidates, Michelot's fixed point beyond),
+// global write is the 28-byte record.  ONE WARP PER MAP, 8 maps per CTA, 2 CTAs (16 warps) per SM; no map
+// is staged in shared memory:
+//   * the warp streams its map through registers (24 coalesced 128-bit loads per lane, issued in
+//     chunks of 6; only the maximum of each float4 is kept),
+//   * max (CREDUX) -> candidate set {z > max - T}: the few float4 that hold a candidate are re-read
+//     (L1 / L2 hits) and ballot-compacted into a short list (a trained head leaves 2-3 pixels, see
+//     SURVEY.md 8c) -> Michelot's fixed point on the list = the exact sort / cumsum threshold of
+//     sparsemax,
 //   * the convolution is evaluated sparsely, C(q) = sum_s w_s g(dy) g(dx) (+ reflected images), only
 //     where the arg max can be - inside the support's bounding box (the OKS kernel is non-negative and
-//     decreasing, so the maximum of C cannot lie outside it): directly at the pixels of a compact box (the box
-//     dilated by one pixel when that fits the warp, so that the sub-pixel stencil comes out of the same pass),
-//     or - scattered supports - by scattering every source's window into a 64 x 48 tile (a small pool of tiles,
-//     taken for the duration of the scatter + scan only) and scanning the rows of the box,
+//     decreasing, so the maximum of C cannot lie outside it): directly at the pixels of a compact box,
+//     or - scattered supports - by scattering every source's window into the warp's
+//     64 x 48 shared-memory tile and scanning the rows of the box,
 //   * all reductions are warp shuffles / redux: no block barrier on this path.
 // Maps that are not sparse (flat random-init logits, arbitrary / negative heatmaps handed to the
-// public codec API) are queued and decoded afterwards by the CTA with a dense separable
+// public codec API) are queued and decoded afterwards by the whole CTA with a dense separable
 // convolution (decode_dense) - correct for any input, just not HBM-bound.
 #include "common.cuh"
-#include "ptx.cuh"
 
 #include <math.h>
 
@@ -43,18 +35,14 @@ namespace pp {
 
 constexpr int kMaxRadius = 9;  // ceil(3 * 3.0): the variance is clipped to <= 3.0
 constexpr int kTaps = 2 * kMaxRadius + 1;
-constexpr int kConsumers = 20;  // consumer warps (one map each at a time)
-constexpr int kStages = 12;     // ring depth: 12-KB stages, held only while a map is streamed and its candidates compacted
-constexpr int kTiles = 4;       // 12-KB scatter tiles for maps with scattered supports (acquired after the stage is released)
-constexpr int kFullBars = 128;  // "landed" barriers, indexed by copy number: >= kConsumers * 2 + kStages (see the kernel)
-constexpr int kDecThreads = 32 * (kConsumers + 1);  // + the producer warp
-constexpr int kDenseWarps = 8;   // the dense path uses 8 warps (3 float4 of the map per thread)
+constexpr int kDecWarps = 8;    // maps per CTA (one warp each)
+constexpr int kDecThreads = 32 * kDecWarps;
+constexpr int kDecCtasPerSm = 2;  // 16 maps in flight per SM
+constexpr int kDenseWarps = kDecWarps;   // the dense path uses the whole CTA (3 float4 of the map per thread)
 constexpr int kDenseThreads = 32 * kDenseWarps;
-constexpr int kListCap = 96;    // candidates per map kept in the compact list
+constexpr int kListCap = 128;   // candidates per map kept in the compact list
 constexpr int kSrcCap = 2 * kListCap;
-constexpr int kBoxPix = 192;    // a bounding box up to this area is evaluated pixel by pixel
-constexpr int kHopPix = 384;    // ... and so are the one-hop boxes of a scattered support up to this many pixels in total
-constexpr int kQueueCap = 512;  // maps per CTA (bounds the dense-path queue)
+constexpr int kBoxPix = 192;    // bounding boxes up to this area are evaluated pixel by pixel
 
 struct DecodeParams {
   const float* maps;
@@ -64,9 +52,7 @@ struct DecodeParams {
   float* records;
   float* merged_out;
   int num_kpts;
-  int count;          // batch * num_kpts maps
-  int items_per_cta;  // contiguous maps per CTA (<= kQueueCap)
-  int probe;          // profiling only (PP_DECODE_PROBE): 1 = consumers only release the stages, 2 = stop after the candidate lists
+  int count;  // batch * num_kpts maps
   int is_logits;
   int temp_is_pow2;
   float temperature, inv_temperature, normalize, err_div;
@@ -338,15 +324,13 @@ __device__ __noinline__ void decode_dense(const DecodeParams& p, int item, float
 }
 
 // =================================================================================================
-// Sparse path: one warp per map, the map staged in shared memory by the producer's bulk copy.
+// Sparse path: one warp per map, the map streamed from global memory straight into registers.
 // =================================================================================================
 struct __align__(16) WarpList {
   float val[kSrcCap];            // candidate / source values
   unsigned short idx[kSrcCap];   // flat pixel index, later (y << 8 | x), of each candidate / source
   float taps[kTaps + 1];         // the map's OKS taps (zero-padded)
   float fac[kTaps + 1];          // weight * row factors of the source being scattered
-  unsigned box[32];              // search boxes (y0 | y1 << 8 | x0 << 16 | x1 << 24)
-  int pre[33];                   // pixels before box i
 };
 
 __device__ __forceinline__ float warp_max_fast(float v) {  // CREDUX.MAX.F32 (sm_100a)
@@ -355,92 +339,89 @@ __device__ __forceinline__ float warp_max_fast(float v) {  // CREDUX.MAX.F32 (sm
   return r;
 }
 
-// 1-D bulk copy global -> shared (async proxy), completion bytes on an mbarrier.
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
-               : "memory");
-}
-// Generic-proxy writes to a stage (the scatter tile) are ordered before the producer's next bulk copy into it.
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ---- code size ----------------------------------------------------------------------------------------------
-// Every map walks this code ONCE, 20 warps per SM are at different places in it, and a straight-line pass over
-// thousands of instructions runs at the speed of the instruction cache refill (measured: 14 000 cycles per map with
-// the loops unrolled and the helpers inlined at every call site, most of it "no instruction" stalls).  Hence: rolled
-// loops wherever four loads in flight are enough, the per-map stages as __noinline__ functions shared by both passes
-// of a TTA call, and the rare paths (more than 32 candidates, scattered supports, the scatter tile) out of line.
-
-// Scans one staged map (H x W fp32, 12 KB): maximum (CREDUX), then the candidates - logits: {z > max - T}, a
-// superset of the sparsemax support; heatmaps: the positive pixels - ballot-compacted into the list at wl[off...] as
-// (y << 8 | x, raw value), x mirrored for the flipped pass.  Deterministic order (float4 index, component, lane).
-// Returns the number of candidates, or -1 when the map is not a case for the sparse path (too many candidates,
-// negative heatmap values).
+// Streams one map (H x W fp32, 12 KB) through the warp's registers - 24 coalesced 128-bit loads per
+// lane, only the maximum of every float4 is kept.  Returns the lane's mask of float4 that hold a
+// candidate - logits: {z > max - T}, a superset of the sparsemax support; heatmaps: the positive
+// pixels - the candidate threshold in `thr` and the maximum in `mx` (logits).  `bad` is set when the
+// map has negative heatmap values (not a case for the sparse path).
 template <int H, int W, bool LOGITS>
-__device__ __noinline__ int scan_map(const DecodeParams& p, const float* smap, WarpList& wl, int off, int mirror, float& mx_out) {
+__device__ __forceinline__ unsigned warp_stream(const DecodeParams& p, const float* gmap, int lane, float& mx, float& thr,
+                                                bool& bad) {
   constexpr int NV = H * W / 128;  // float4 per lane
-  static_assert(NV <= 32 && W % 4 == 0, "one candidate bit per float4 of the lane; a float4 never straddles two rows");
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const float4* s4 = reinterpret_cast<const float4*>(smap) + lane;
-  // the one place where full unrolling pays: 24 independent 128-bit loads in flight, only the maximum of each kept
+  constexpr int CH = 6;            // loads in flight per lane and chunk
+  static_assert(NV % CH == 0 && NV <= 32, "map must split into whole chunks of float4 per lane");
+  const float4* g4 = reinterpret_cast<const float4*>(gmap) + lane;
   float m4[NV];
   float lo = 0.f;
+  mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const float4 q = s4[32 * j];
-    m4[j] = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
-    if (!LOGITS) lo = fminf(fminf(lo, q.x), fminf(fminf(q.y, q.z), q.w));
+  for (int c = 0; c < NV; c += CH) {
+    float4 q[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) q[i] = __ldg(g4 + 32 * (c + i));
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      m4[c + i] = fmaxf(fmaxf(q[i].x, q[i].y), fmaxf(q[i].z, q[i].w));
+      if (!LOGITS) lo = fminf(fminf(lo, q[i].x), fminf(fminf(q[i].y, q[i].z), q[i].w));
+    }
   }
-  float mx = -INFINITY, thr = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; j += 2) mx = fmaxf(mx, fmaxf(m4[j], m4[j + 1]));
+  thr = 0.f;
+  bad = false;
   if (LOGITS) {
     mx = warp_max_fast(mx);
     // candidates: z / T > max / T - 1.  The raw-domain test is made slightly generous (any superset
     // of the support gives the same threshold); the exact scaled values are formed per candidate.
     thr = mx - p.temperature * 1.000001f - 1e-30f;
-  } else if (__any_sync(0xffffffffu, lo < 0.f)) {
-    return -1;  // negative values break the "maximum lies inside the support's bounding box" argument
+  } else {
+    // negative values break the "maximum lies inside the support's bounding box" argument
+    bad = __any_sync(0xffffffffu, lo < 0.f);
   }
-  mx_out = mx;
   unsigned bits = 0;
 #pragma unroll
   for (int j = 0; j < NV; ++j) bits |= (m4[j] > thr ? 1u : 0u) << j;
-  // in rounds, every lane re-reads its next float4 that holds a candidate; ballot compaction keeps the list order
-  // deterministic (round, component, lane)
+  return bits;
+}
+
+// Compacts the candidates of a streamed map into the list (idx, raw val) at list[off...]: in rounds,
+// every lane re-reads its next float4 that holds a candidate (L1 / L2 hits); ballot compaction keeps
+// the list order deterministic (round, component, lane).  Returns the number of entries, or -1 when
+// there are too many for this path.
+__device__ __forceinline__ int warp_compact(const float* gmap, unsigned bits, float thr, WarpList& wl, int off, int lane) {
+  const float4* g4 = reinterpret_cast<const float4*>(gmap) + lane;
+  const unsigned lt_mask = (1u << lane) - 1u;
   int n = 0;
-#pragma unroll 1
   while (__any_sync(0xffffffffu, bits != 0u)) {
     const int j = __ffs(bits) - 1;
     float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    if (bits) q = s4[32 * j];
+    if (bits) q = __ldg(g4 + 32 * j);
     bits &= bits - 1u;
-    const int pix = (lane + 32 * j) * 4, y = pix / W, x = pix % W;
     const float e[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const bool take = e[c] > thr;
       const unsigned bal = __ballot_sync(0xffffffffu, take);
       const int add = __popc(bal);
-      if (take && n + add <= kListCap) {  // on overflow only the count keeps growing
-        const int pos = off + n + __popc(bal & lt_mask);
-        wl.val[pos] = e[c];
-        wl.idx[pos] = (unsigned short)((y << 8) | (mirror ? W - 1 - (x + c) : x + c));
+      if (n + add <= kListCap) {  // warp-uniform; on overflow only the count keeps growing
+        if (take) {
+          const int pos = off + n + __popc(bal & lt_mask);
+          wl.val[pos] = e[c];
+          wl.idx[pos] = (unsigned short)((lane + 32 * j) * 4 + c);
+        }
       }
       n += add;
     }
-    if (n > kListCap) return -1;  // does not fit: not sparse
+    if (n > kListCap) break;  // does not fit: not sparse
   }
   __syncwarp();
-  return n;
+  return n > kListCap ? -1 : n;
 }
 
-// More than 32 candidates (rare): tau <- (sum_{z > tau} z - 1) / #{z > tau} until the set stops shrinking (Michelot)
-// = the sort / cumsum threshold of Martins & Astudillo, Alg. 1 (on z - max z).
+// List entries (pixel index, raw value) -> (y << 8 | x, heatmap value): sparsemax threshold by
+// Michelot's fixed point on the list (logits), mirror of the flipped pass.
 // Keeps the non-zero entries of list[off, off + n), order preserved; returns how many.
-__device__ __forceinline__ int keep_support(WarpList& ws, int off, int n) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ int keep_support(WarpList& ws, int off, int n, int lane) {
   const unsigned lt_mask = (1u << lane) - 1u;
   int nnz = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
@@ -460,69 +441,77 @@ __device__ __forceinline__ int keep_support(WarpList& ws, int off, int n) {
   return nnz;
 }
 
-__device__ __noinline__ void sparsemax_list_big(const DecodeParams& p, WarpList& ws, int off, int n, float mx) {
-  const int lane = threadIdx.x & 31;
-  const float mxs = p.temp_is_pow2 ? mx * p.inv_temperature : mx / p.temperature;
-  auto scaled = [&](float e) { return (p.temp_is_pow2 ? e * p.inv_temperature : e / p.temperature) - mxs; };
-  float thr2 = -1.f, tau = -1.f;
-  int prev = -1;
-  for (int it = 0; it < kListCap + 2; ++it) {
-    float sum = 0.f;
-    int cnt = 0;
-    for (int i = lane; i < n; i += 32) {
-      const float z = scaled(ws.val[off + i]);
-      if (z > thr2) { sum += z; ++cnt; }
+// Returns the length of the list after it has shrunk to its support (logits) / unchanged (heatmaps).
+template <int H, int W, bool LOGITS>
+__device__ __forceinline__ int warp_finish_list(const DecodeParams& p, WarpList& ws, int off, int n, int mirror, float mx,
+                                                int lane) {
+  for (int i = lane; i < n; i += 32) {
+    const int px = ws.idx[off + i];
+    const int y = px / W, x = px % W;
+    ws.idx[off + i] = (unsigned short)((y << 8) | (mirror ? W - 1 - x : x));
+  }
+  if (LOGITS) {
+    // tau <- (sum_{z > tau} z - 1) / #{z > tau} until the set stops shrinking = the sort / cumsum
+    // threshold of Martins & Astudillo, Alg. 1 (on z - max z).
+    const float mxs = p.temp_is_pow2 ? mx * p.inv_temperature : mx / p.temperature;
+    auto scaled = [&](float e) { return (p.temp_is_pow2 ? e * p.inv_temperature : e / p.temperature) - mxs; };
+    float tau = -1.f;
+    if (n <= 32) {
+      // the usual case, one candidate per lane: Martins & Astudillo Alg. 1 without the sort and without a
+      // data-dependent iteration count - lane i counts k_i = #{z_j >= z_i} and S_i = sum of those z_j (= its position and
+      // prefix sum in the sorted order; tied values share both), is in the support iff 1 + k_i z_i > S_i, and
+      // tau = (S - 1) / k of the smallest supported value.  One pass over the list in shared memory.
+      const float zi = lane < n ? scaled(ws.val[off + lane]) : -INFINITY;
+      int k = 0;
+      float sum = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float zj = scaled(ws.val[off + j]);
+        if (zj >= zi) { ++k; sum += zj; }
+      }
+      const bool in = lane < n && (1.f + (float)k * zi > sum);
+      const int kstar = __reduce_max_sync(0xffffffffu, in ? k : 0);  // >= 1: the maximum (z == 0) is always supported
+      const unsigned who = __ballot_sync(0xffffffffu, in && k == kstar);
+      const float sstar = __shfl_sync(0xffffffffu, sum, __ffs(who) - 1);
+      tau = (sstar - 1.f) / (float)kstar;
+      const float v = lane < n ? fminf(fmaxf(fmaxf(zi - tau, 0.f) * p.normalize, 0.f), 1.f) : 0.f;
+      const unsigned short yx = lane < n ? ws.idx[off + lane] : (unsigned short)0;
+      const unsigned bal = __ballot_sync(0xffffffffu, v != 0.f);
+      __syncwarp();  // every lane has read the raw values and its index
+      if (v != 0.f) {
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        ws.val[pos] = v;
+        ws.idx[pos] = yx;
+      }
+      __syncwarp();
+      return __popc(bal);
+    } else {
+      float zc[kListCap / 32];
+#pragma unroll
+      for (int i = 0; i < kListCap / 32; ++i) zc[i] = (lane + 32 * i < n) ? scaled(ws.val[off + lane + 32 * i]) : -INFINITY;
+      float thr2 = -1.f;
+      int prev = -1;
+      for (int it = 0; it < kListCap + 2; ++it) {
+        float sum = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < kListCap / 32; ++i)
+          if (zc[i] > thr2) { sum += zc[i]; ++cnt; }
+        sum = warp_sum(sum);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        tau = (sum - 1.f) / (float)cnt;
+        if (cnt == prev) break;
+        prev = cnt;
+        thr2 = fmaxf(thr2, tau);
+      }
+#pragma unroll
+      for (int i = 0; i < kListCap / 32; ++i)
+        if (lane + 32 * i < n) ws.val[off + lane + 32 * i] = fminf(fmaxf(fmaxf(zc[i] - tau, 0.f) * p.normalize, 0.f), 1.f);
+      __syncwarp();
+      return keep_support(ws, off, n, lane);
     }
-    sum = warp_sum(sum);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    tau = (sum - 1.f) / (float)cnt;  // cnt >= 1: the maximum (z == 0) is always a candidate
-    if (cnt == prev) break;
-    prev = cnt;
-    thr2 = fmaxf(thr2, tau);
-  }
-  for (int i = lane; i < n; i += 32)
-    ws.val[off + i] = fminf(fmaxf(fmaxf(scaled(ws.val[off + i]) - tau, 0.f) * p.normalize, 0.f), 1.f);
-  __syncwarp();
-}
-
-// Raw candidate values -> heatmap values: exact sparsemax threshold on the list; the list shrinks to its support
-// (returns the new length).
-__device__ __noinline__ int sparsemax_list(const DecodeParams& p, WarpList& ws, int off, int n, float mx) {
-  if (n > 32) {
-    sparsemax_list_big(p, ws, off, n, mx);
-    return keep_support(ws, off, n);
-  }
-  // the usual case, one candidate per lane: Martins & Astudillo Alg. 1 without the sort - lane i counts
-  // k_i = #{z_j >= z_i} and S_i = sum of those z_j (= its position and prefix sum in the sorted order; tied
-  // values share both), is in the support iff 1 + k_i z_i > S_i, and tau = (S - 1) / k of the smallest
-  // supported value.  No data-dependent iteration count: one pass over the list in shared memory.
-  const int lane = threadIdx.x & 31;
-  const float mxs = p.temp_is_pow2 ? mx * p.inv_temperature : mx / p.temperature;
-  auto scaled = [&](float e) { return (p.temp_is_pow2 ? e * p.inv_temperature : e / p.temperature) - mxs; };
-  const float zi = lane < n ? scaled(ws.val[off + lane]) : -INFINITY;
-  int k = 0;
-  float sum = 0.f;
-#pragma unroll 2
-  for (int j = 0; j < n; ++j) {
-    const float zj = scaled(ws.val[off + j]);
-    if (zj >= zi) { ++k; sum += zj; }
-  }
-  const bool in = lane < n && (1.f + (float)k * zi > sum);
-  const int kstar = __reduce_max_sync(0xffffffffu, in ? k : 0);  // >= 1: the maximum (z == 0) is always supported
-  const unsigned who = __ballot_sync(0xffffffffu, in && k == kstar);
-  const float sstar = __shfl_sync(0xffffffffu, sum, __ffs(who) - 1);
-  const float tau = (sstar - 1.f) / (float)kstar;
-  const float v = lane < n ? fminf(fmaxf(fmaxf(zi - tau, 0.f) * p.normalize, 0.f), 1.f) : 0.f;
-  const unsigned short yx = lane < n ? ws.idx[off + lane] : (unsigned short)0;
-  const unsigned bal = __ballot_sync(0xffffffffu, v != 0.f);
-  __syncwarp();  // every lane has read the raw values and its index
-  if (v != 0.f) {
-    const int pos = off + __popc(bal & ((1u << lane) - 1u));
-    ws.val[pos] = v;
-    ws.idx[pos] = yx;
   }
   __syncwarp();
-  return __popc(bal);
+  return n;
 }
 
 // First maximum of (value, flat index) pairs over the warp: CREDUX for the value, then the lowest index among the
@@ -533,213 +522,39 @@ __device__ __forceinline__ void warp_first_max(float& best, int& best_i) {
   best = m;
 }
 
-#ifdef PP_DECODE_TIMING
-// Debug build only: per-phase cycle totals of the sparse decode (lane 0 of every consumer warp), read back through
-// pp_debug_decode_timing().  [0] items, [1] wait for the stage(s), [2] scan (map), [3] scan (flipped map),
-// [4] sparsemax + merge + support, [5] search set-up, [6] evaluation / tile, [7] everything after the scans.
-__device__ unsigned long long g_dec_timing[8];
-#define PP_T(var) const long long var = clock64()
-#define PP_TADD(slot, a, b) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_dec_timing[slot], (unsigned long long)((b) - (a))); } while (0)
-#else
-#define PP_T(var)
-#define PP_TADD(slot, a, b)
-#endif
-
-// Scatter tiles: a bit mask of free tiles in shared memory; a warp takes one for its scatter + scan only.
-__device__ __forceinline__ int tile_acquire(unsigned* free_mask, int lane) {
-  int t = 0;
-  if (lane == 0) {
-    for (;;) {
-      const unsigned m = *reinterpret_cast<volatile unsigned*>(free_mask);
-      if (m == 0u) { __nanosleep(100); continue; }
-      t = __ffs(m) - 1;
-      if (atomicAnd(free_mask, ~(1u << t)) & (1u << t)) break;
-    }
-  }
-  return __shfl_sync(0xffffffffu, t, 0);
-}
-__device__ __forceinline__ void tile_release(unsigned* free_mask, int t, int lane) {
-  __syncwarp();
-  if (lane == 0) atomicOr(free_mask, 1u << t);
-}
-
-struct Support {  // the merged map's non-zero pixels: ws.val / ws.idx [0, nnz), bounding box, the keypoint's OKS radius
-  int nnz, ymin, ymax, xmin, xmax, rad;
-};
-
-__device__ __forceinline__ float oks_tap(const WarpList& ws, int rad, int d) {  // g(d), 0 for d > rad (zero-padded table)
-  return ws.taps[rad + min(d, rad + 1)];
-}
-
-// The box of the arg max is extended to the border where a reflected image can pull the maximum outwards.
-template <int H, int W>
-__device__ __forceinline__ void extend_box(int rad, int& y0, int& y1, int& x0, int& x1) {
-  if (y0 <= rad - 1) y0 = 0;
-  if (y1 >= H - rad) y1 = H - 1;
-  if (x0 <= rad - 1) x0 = 0;
-  if (x1 >= W - rad) x1 = W - 1;
-}
-
-// Scattered support: for every source the box of the sources whose windows can overlap its own (Chebyshev
-// distance <= 2 rad).  Any pixel q sees only sources that are mutual neighbours (all within rad of q); moving q
-// into their box does not decrease any of their terms and the others are >= 0 - so the maximum over the union of
-// these one-hop boxes is the global one, no connected components needed.  An isolated source contributes a single
-// pixel.  Boxes contained in another source's box are dropped.  Fills ws.box / ws.pre, returns the pixel total.
-template <int H, int W>
-__device__ __noinline__ int one_hop_boxes(WarpList& ws, const Support& sp) {
-  const int lane = threadIdx.x & 31, nnz = sp.nnz, rad = sp.rad;
-  int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
-  if (lane < nnz) {
-    const int yx = ws.idx[lane];
-    const int sy = yx >> 8, sx = yx & 255;
-    y0 = y1 = sy; x0 = x1 = sx;
-    for (int j = 0; j < nnz; ++j) {
-      const int o = ws.idx[j], oy = o >> 8, ox = o & 255;
-      if (abs(oy - sy) <= 2 * rad && abs(ox - sx) <= 2 * rad) {
-        y0 = min(y0, oy); y1 = max(y1, oy); x0 = min(x0, ox); x1 = max(x1, ox);
-      }
-    }
-    extend_box<H, W>(rad, y0, y1, x0, x1);
-    ws.box[lane] = (unsigned)y0 | ((unsigned)y1 << 8) | ((unsigned)x0 << 16) | ((unsigned)x1 << 24);
-  }
-  __syncwarp();
-  int my_area = 0;
-  if (lane < nnz) {
-    bool drop = false;
-    for (int j = 0; j < nnz; ++j) {
-      const unsigned o = ws.box[j];
-      const int oy0 = o & 255, oy1 = (o >> 8) & 255, ox0 = (o >> 16) & 255, ox1 = o >> 24;
-      const bool inside = oy0 <= y0 && oy1 >= y1 && ox0 <= x0 && ox1 >= x1;
-      const bool same = oy0 == y0 && oy1 == y1 && ox0 == x0 && ox1 == x1;
-      drop |= j != lane && inside && (!same || j < lane);
-    }
-    my_area = drop ? 0 : (y1 - y0 + 1) * (x1 - x0 + 1);
-  }
-  int incl = my_area;  // inclusive prefix sum over the lanes
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane < nnz) ws.pre[lane + 1] = incl;
-  if (lane == 0) ws.pre[0] = 0;
-  __syncwarp();
-  return __shfl_sync(0xffffffffu, incl, 31);
-}
-
-// Scatter tile (big overlapping windows): every source adds w * g(dy) g(dx) (+ reflections) into a 64 x 48 tile
-// from the pool; first arg max over the rows of the search box, the sub-pixel stencil straight out of the tile.
-// Returns true when the stencil is valid.
-template <int H, int W>
-__device__ __noinline__ bool tile_search(WarpList& ws, const Support& sp, int sy0, int sy1, float* tiles, unsigned* tile_mask,
-                                         float& best, int& best_i, float (&st)[5]) {
-  const int lane = threadIdx.x & 31, rad = sp.rad;
-  const int tile_id = tile_acquire(tile_mask, lane);
-  float* tile = tiles + (size_t)tile_id * (H * W);
-  const int zy0 = max(0, sp.ymin - rad - 1), zy1 = min(H - 1, sp.ymax + rad + 1);
-  float4* t4 = reinterpret_cast<float4*>(tile);
-  for (int i = zy0 * (W / 4) + lane; i < (zy1 + 1) * (W / 4); i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncwarp();
-#pragma unroll 1
-  for (int s = 0; s < sp.nnz; ++s) {
-    const float w = ws.val[s];
-    const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
-    const int y0 = max(0, sy - rad), y1 = min(H - 1, sy + rad), x0 = max(0, sx - rad), x1 = min(W - 1, sx + rad);
-    // 1-D factors over the window: the direct tap plus the taps of the two reflected images (only where a
-    // reflected image is within the radius: warp-uniform tests); rows carry the weight, lanes keep their
-    // column factor in a register
-    float fx = 0.f;
-    if (lane <= 2 * rad) {
-      const int yy = y0 + lane, xx = x0 + lane;
-      if (yy <= y1) {
-        float fy = oks_tap(ws, rad, abs(yy - sy));
-        if (sy < rad || sy >= H - rad) fy = fy + oks_tap(ws, rad, yy + 1 + sy) + oks_tap(ws, rad, 2 * H - 1 - sy - yy);
-        ws.fac[lane] = __fmul_rn(w, fy);
-      }
-      if (xx <= x1) {
-        fx = oks_tap(ws, rad, abs(xx - sx));
-        if (sx < rad || sx >= W - rad) fx = fx + oks_tap(ws, rad, xx + 1 + sx) + oks_tap(ws, rad, 2 * W - 1 - sx - xx);
-      }
-    }
-    __syncwarp();
-    if (x0 + lane <= x1) {  // lane = window column; the window rows are independent read-modify-writes
-      float* c = tile + y0 * W + x0 + lane;
-      const int rows = y1 - y0 + 1;
-      int dy = 0;
-#pragma unroll 1
-      for (; dy + 4 <= rows; dy += 4) {  // four rows in flight
-        const float c0 = c[dy * W], c1 = c[(dy + 1) * W], c2 = c[(dy + 2) * W], c3 = c[(dy + 3) * W];
-        const float f0 = ws.fac[dy], f1 = ws.fac[dy + 1], f2 = ws.fac[dy + 2], f3 = ws.fac[dy + 3];
-        c[dy * W] = __fadd_rn(c0, __fmul_rn(f0, fx));
-        c[(dy + 1) * W] = __fadd_rn(c1, __fmul_rn(f1, fx));
-        c[(dy + 2) * W] = __fadd_rn(c2, __fmul_rn(f2, fx));
-        c[(dy + 3) * W] = __fadd_rn(c3, __fmul_rn(f3, fx));
-      }
-#pragma unroll 1
-      for (; dy < rows; ++dy) c[dy * W] = __fadd_rn(c[dy * W], __fmul_rn(ws.fac[dy], fx));
-    }
-    __syncwarp();
-  }
-  // the maximum of each float4 first, the component only on a new best
-#pragma unroll 2
-  for (int i = sy0 * (W / 4) + lane; i < (sy1 + 1) * (W / 4); i += 32) {
-    const float4 c = t4[i];
-    const float m = fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w));
-    if (m > best) {
-      best = m;
-      best_i = 4 * i + (c.x == m ? 0 : (c.y == m ? 1 : (c.z == m ? 2 : 3)));
-    }
-  }
-  warp_first_max(best, best_i);
-  bool have = false;
-  if (best > 0.f) {
-    const int ys = best_i / W, xs = best_i % W;
-    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {  // same sums, same order as any other evaluation of C
-      st[0] = tile[best_i]; st[1] = tile[best_i - 1]; st[2] = tile[best_i + 1]; st[3] = tile[best_i - W]; st[4] = tile[best_i + W];
-      have = true;
-    }
-  }
-  tile_release(tile_mask, tile_id, lane);
-  return have;
-}
-
-// The sparse decode of one map whose stage(s) have landed.  `release(which)` hands stage 0 (the map) / 1 (the
-// flipped pass's map) back to the producer as soon as its candidates are in the list; every stage is released
-// exactly once on every path.  Returns false when the map has to go through the dense path.
-template <int H, int W, bool LOGITS, typename Release>
-__device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, WarpList& ws, int lane, const float* stage1,
-                                              const float* stage2, float* tiles, unsigned* tile_mask, Release&& release) {
+// The sparse decode of one map.  Returns false when the map has to go through the dense path.
+template <int H, int W, bool LOGITS>
+__device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, WarpList& ws, int lane, float* tile) {
   constexpr int NPX = H * W;
   const int K = p.num_kpts;
   const int b = item / K, k = item % K;
   const bool tta = p.maps_flip != nullptr;
   const int kf = tta ? p.flip_idx[k] : k;
   const unsigned lt_mask = (1u << lane) - 1u;
-  Support sp;
-  sp.rad = p.radius[k];
-  const int rad = sp.rad;
+  const float* map1 = p.maps + (size_t)item * NPX;
+  const float* map2 = tta ? p.maps_flip + (size_t)(b * K + kf) * NPX : nullptr;
+  const int rad = p.radius[k];
   if (lane < kTaps + 1) ws.taps[lane] = p.taps[k][lane];  // read after the __syncwarp()s of the list stages
 
-  float mx1 = 0.f, mx2 = 0.f;
-  PP_T(t_a0);
-  const int n1 = scan_map<H, W, LOGITS>(p, stage1, ws, 0, 0, mx1);
-  release(0);  // the map's candidates are in the list (or the map goes to the dense path)
-  PP_T(t_a1);
-  PP_TADD(2, t_a0, t_a1);
+  float mx1, mx2 = 0.f, thr1, thr2 = 0.f;
+  bool bad1, bad2 = false;
+  const unsigned bits1 = warp_stream<H, W, LOGITS>(p, map1, lane, mx1, thr1, bad1);
+  unsigned bits2 = 0;
+  if (tta) bits2 = warp_stream<H, W, LOGITS>(p, map2, lane, mx2, thr2, bad2);
+  if (bad1 || bad2) return false;
+
+  const int n1 = warp_compact(map1, bits1, thr1, ws, 0, lane);
+  if (n1 < 0) return false;
   int n2 = 0;
   if (tta) {
-    if (n1 >= 0) n2 = scan_map<H, W, LOGITS>(p, stage2, ws, n1, 1, mx2);
-    release(1);
+    n2 = warp_compact(map2, bits2, thr2, ws, n1, lane);
+    if (n2 < 0) return false;
   }
-  PP_T(t_a2);
-  PP_TADD(3, t_a1, t_a2);
-  if (n1 < 0 || n2 < 0) return false;
-  if (p.probe == 2) return true;
-  // both lists shrink to their supports first (a random-init head: ~15 candidates, ~4 supported), list 2 stays at n1
-  const int m1 = LOGITS ? sparsemax_list(p, ws, 0, n1, mx1) : n1;
+  // both lists shrink to their supports first (a random-init head: ~15 candidates, ~4 supported); list 2 stays at n1
+  const int m1 = warp_finish_list<H, W, LOGITS>(p, ws, 0, n1, 0, mx1, lane);
   int n = m1;
   if (tta) {
-    const int m2 = LOGITS ? sparsemax_list(p, ws, n1, n2, mx2) : n2;
+    const int m2 = warp_finish_list<H, W, LOGITS>(p, ws, n1, n2, 1, mx2, lane);
     // merged = (P + mirror(Pf)) * 0.5, pixel by pixel in fp32 exactly like the reference: an entry of
     // the first list absorbs the matching entry of the second; unmatched entries are halved on their own
     for (int i = lane; i < m1; i += 32) {
@@ -749,7 +564,7 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
       ws.val[i] = (ws.val[i] + other) * 0.5f;
     }
     __syncwarp();  // list-2 values are read above and rewritten below
-    for (int i0 = 0; i0 < m2; i0 += 32) {  // unmatched entries of list 2 move up behind list 1
+    for (int i0 = 0; i0 < m2; i0 += 32) {  // unmatched entries of list 2 move up behind list 1 (matched ones as zeros)
       const int i = i0 + lane;
       float v = 0.f;
       unsigned short yx = 0;
@@ -759,13 +574,11 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
         for (int j = 0; j < m1; ++j) dup |= ws.idx[j] == yx;
         v = dup ? 0.f : (0.f + ws.val[n1 + i]) * 0.5f;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, i < m2);
-      __syncwarp();
+      __syncwarp();  // m1 + i <= n1 + i: a chunk never overwrites an entry a later chunk still has to read
       if (i < m2) {
-        ws.val[m1 + i] = v;  // m1 + i <= n1 + i: never ahead of an unread entry of this or a later chunk
+        ws.val[m1 + i] = v;
         ws.idx[m1 + i] = yx;
       }
-      (void)bal;
       __syncwarp();
     }
     n = m1 + m2;
@@ -793,131 +606,137 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
   __syncwarp();
   ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
   xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-  sp.nnz = nnz; sp.ymin = ymin; sp.ymax = ymax; sp.xmin = xmin; sp.xmax = xmax;
   const bool nonempty = nnz > 0;
-  PP_T(t_b0);
-  PP_TADD(4, t_a2, t_b0);
 
+  const float* gt = ws.taps + rad;
+  auto g = [&](int d) { return gt[min(d, rad + 1)]; };  // g(d), 0 for d > rad (the table is zero-padded)
   int best_i = 0;
   float conf = 0.f, lx = 0.f, ly = 0.f;
   if (nonempty) {
+    // C = sum_s w_s g(dy) g(dx) (+ the reflected images at -1 - s and 2H - 1 - s), evaluated directly
+    auto eval_c = [&](int qy, int qx) -> float {
+      float acc = 0.f;
+      for (int s = 0; s < nnz; ++s) {
+        const float w = ws.val[s];
+        const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
+        float fy = g(abs(qy - sy));
+        float fx = g(abs(qx - sx));
+        if (sy < rad || sy >= H - rad) {  // warp-uniform test
+          fy += g(qy + 1 + sy);
+          fy += g(2 * H - 1 - sy - qy);
+        }
+        if (sx < rad || sx >= W - rad) {
+          fx += g(qx + 1 + sx);
+          fx += g(2 * W - 1 - sx - qx);
+        }
+        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(w, fy), fx));
+      }
+      return acc;
+    };
     // The arg max of C lies inside the support's bounding box (the OKS kernel is non-negative and
     // decreasing in |d|), extended to the border where a reflected image can pull it outwards.
-    int sy0 = ymin, sy1 = ymax, sx0 = xmin, sx1 = xmax;
-    extend_box<H, W>(rad, sy0, sy1, sx0, sx1);
-    const int area = (sy1 - sy0 + 1) * (sx1 - sx0 + 1);
+    const int sy0 = ymin <= rad - 1 ? 0 : ymin, sy1 = ymax >= H - rad ? H - 1 : ymax;
+    const int sx0 = xmin <= rad - 1 ? 0 : xmin, sx1 = xmax >= W - rad ? W - 1 : xmax;
+    const int bw = sx1 - sx0 + 1, area = (sy1 - sy0 + 1) * bw;
     float best = -INFINITY;
     best_i = 0x7fffffff;
     bool have_stencil = false;
-    float st[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // C at the peak, left, right, up, down
-
-    // ---- where to look: a list of boxes (packed y0 | y1 << 8 | x0 << 16 | x1 << 24 in ws.box, running pixel counts in
-    // ws.pre) that is guaranteed to hold the arg max: compact support - the bounding box itself (dilated by one pixel
-    // when that fits the warp, so that one evaluation pass also yields the four neighbours of the sub-pixel step);
-    // scattered support - one_hop_boxes(); too many pixels that way - the scatter tile.
-    int total = 0, nboxes = 1;
-    bool fused = false;  // single dilated box of <= 32 pixels
-    bool use_tile = false;
+    float st_c = 0.f, st_l = 0.f, st_r = 0.f, st_u = 0.f, st_d = 0.f;
     if (area <= kBoxPix) {
-      int dy0 = max(0, sy0 - 1), dy1 = min(H - 1, sy1 + 1), dx0 = max(0, sx0 - 1), dx1 = min(W - 1, sx1 + 1);
-      fused = (dy1 - dy0 + 1) * (dx1 - dx0 + 1) <= 32;
-      if (!fused) { dy0 = sy0; dy1 = sy1; dx0 = sx0; dx1 = sx1; }
-      total = (dy1 - dy0 + 1) * (dx1 - dx0 + 1);
-      if (lane == 0) {
-        ws.box[0] = (unsigned)dy0 | ((unsigned)dy1 << 8) | ((unsigned)dx0 << 16) | ((unsigned)dx1 << 24);
-        ws.pre[0] = 0;
-        ws.pre[1] = total;
-      }
-      __syncwarp();
-    } else if (nnz <= 32) {
-      total = one_hop_boxes<H, W>(ws, sp);
-      nboxes = nnz;
-      use_tile = total > (p.probe >= 100 ? p.probe - 100 : kHopPix);
-    } else {
-      use_tile = true;
-    }
-    PP_T(t_b1);
-    PP_TADD(5, t_b0, t_b1);
-
-    if (!use_tile) {
-      // one loop evaluates the pixels of the box list in rounds of 32 and, in a last extra round, the five pixels of
-      // the sub-pixel stencil (unless the fused case already has them): the evaluation of
-      // C = sum_s w_s g(dy) g(dx) (+ the reflected images at -1 - s and 2H - 1 - s) exists once in the code
-      const int rounds = (total + 31) >> 5;
-      float c_fused = 0.f;
-      int fdy0 = 0, fdx0 = 0, fdw = 1;
-#pragma unroll 1
-      for (int r = 0; r <= rounds; ++r) {
-        int qy, qx;
-        bool valid = false;
-        if (r < rounds) {
-          const int gi = min(r * 32 + lane, total - 1);  // a duplicate of the last pixel never wins a tie
-          int bsel = 0;
-          while (bsel + 1 < nboxes && gi >= ws.pre[bsel + 1]) ++bsel;
-          const unsigned bb = ws.box[bsel];
-          const int y0 = bb & 255, x0 = (bb >> 16) & 255, bw = (int)(bb >> 24) - x0 + 1;
-          const int li = gi - ws.pre[bsel];
-          const int row = (int)(((float)li + 0.5f) * __frcp_rn((float)bw));  // exact: li < 4096, bw <= 48
-          qy = y0 + row;
-          qx = x0 + li - row * bw;
-          valid = !fused || (qy >= sy0 && qy <= sy1 && qx >= sx0 && qx <= sx1);  // the dilation ring is not a candidate
-          if (fused) { fdy0 = y0; fdx0 = x0; fdw = bw; }
-        } else {
-          if (have_stencil || !(best > 0.f)) break;
+      // ---- compact support: every pixel of the box.  When the box dilated by one pixel (clamped to the map) fits the
+      // warp, ONE evaluation pass yields the arg max and its four neighbours for the sub-pixel step ----
+      const int dy0 = max(0, sy0 - 1), dy1 = min(H - 1, sy1 + 1), dx0 = max(0, sx0 - 1), dx1 = min(W - 1, sx1 + 1);
+      const int dw = dx1 - dx0 + 1, darea = (dy1 - dy0 + 1) * dw;
+      if (darea <= 32) {
+        const int q = min(lane, darea - 1);
+        const int qy = dy0 + q / dw, qx = dx0 + q % dw;
+        const float c = eval_c(qy, qx);
+        const bool inner = lane < darea && qy >= sy0 && qy <= sy1 && qx >= sx0 && qx <= sx1;  // the ring is not a candidate
+        best = inner ? c : -INFINITY;
+        best_i = inner ? qy * W + qx : 0x7fffffff;
+        warp_first_max(best, best_i);
+        if (best > 0.f) {
           const int ys = best_i / W, xs = best_i % W;
-          if (!(xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1)) break;
-          // lanes 0..4: centre, left, right, up, down
-          qx = xs + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
-          qy = ys + (lane == 3 ? -1 : (lane == 4 ? 1 : 0));
+          if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {  // the four neighbours lie inside the dilated box
+            const int li = (ys - dy0) * dw + (xs - dx0);
+            st_c = __shfl_sync(0xffffffffu, c, li); st_l = __shfl_sync(0xffffffffu, c, li - 1); st_r = __shfl_sync(0xffffffffu, c, li + 1);
+            st_u = __shfl_sync(0xffffffffu, c, li - dw); st_d = __shfl_sync(0xffffffffu, c, li + dw);
+            have_stencil = true;
+          }
         }
-        float c = 0.f;
-#pragma unroll 1
-        for (int s = 0; s < nnz; ++s) {
-          const float w = ws.val[s];
-          const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
-          float fy = oks_tap(ws, rad, abs(qy - sy));
-          float fx = oks_tap(ws, rad, abs(qx - sx));
-          if (sy < rad || sy >= H - rad) {  // warp-uniform test
-            fy += oks_tap(ws, rad, qy + 1 + sy);
-            fy += oks_tap(ws, rad, 2 * H - 1 - sy - qy);
-          }
-          if (sx < rad || sx >= W - rad) {
-            fx += oks_tap(ws, rad, qx + 1 + sx);
-            fx += oks_tap(ws, rad, 2 * W - 1 - sx - qx);
-          }
-          c = __fadd_rn(c, __fmul_rn(__fmul_rn(w, fy), fx));
+      } else {
+        for (int q0 = 0; q0 < area; q0 += 32) {
+          const int q = min(q0 + lane, area - 1);  // the duplicate of the last pixel never wins a tie
+          const int qy = sy0 + q / bw, qx = sx0 + q % bw;
+          const float c = eval_c(qy, qx);
+          if (c > best) { best = c; best_i = qy * W + qx; }
         }
-        if (r < rounds) {
-          if (valid && c > best) { best = c; best_i = qy * W + qx; }
-          if (fused) c_fused = c;
-          if (r == rounds - 1) {
-            warp_first_max(best, best_i);
-            if (fused && best > 0.f) {
-              const int ys = best_i / W, xs = best_i % W;
-              if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {  // the four neighbours lie inside the dilated box
-                const int li = (ys - fdy0) * fdw + (xs - fdx0);
-                st[0] = __shfl_sync(0xffffffffu, c_fused, li); st[1] = __shfl_sync(0xffffffffu, c_fused, li - 1);
-                st[2] = __shfl_sync(0xffffffffu, c_fused, li + 1); st[3] = __shfl_sync(0xffffffffu, c_fused, li - fdw);
-                st[4] = __shfl_sync(0xffffffffu, c_fused, li + fdw);
-                have_stencil = true;
-              }
-            }
-          }
-        } else {
+        warp_first_max(best, best_i);
+      }
+    } else {
+      // ---- scattered support: every source adds w * g(dy) g(dx) (+ reflections) into the warp's 64 x 48
+      // tile; the arg max is searched over the rows of the box ----
+      // (measured: a pool of 3 tiles per 8 warps at twice the occupancy loses more to waiting than it gains)
+      const int zy0 = max(0, ymin - rad - 1), zy1 = min(H - 1, ymax + rad + 1);
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      for (int i = zy0 * (W / 4) + lane; i < (zy1 + 1) * (W / 4); i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      for (int s = 0; s < nnz; ++s) {
+        const float w = ws.val[s];
+        const int yx = ws.idx[s], sy = yx >> 8, sx = yx & 255;
+        const int y0 = max(0, sy - rad), y1 = min(H - 1, sy + rad), x0 = max(0, sx - rad), x1 = min(W - 1, sx + rad);
+        // 1-D factors over the window: the direct tap plus the taps of the two reflected images;
+        // rows carry the weight, lanes keep their column factor in a register
+        float fx = 0.f;
+        if (lane <= 2 * rad) {
+          const int yy = y0 + lane, xx = x0 + lane;
+          if (yy <= y1) ws.fac[lane] = __fmul_rn(w, g(abs(yy - sy)) + g(yy + 1 + sy) + g(2 * H - 1 - sy - yy));
+          if (xx <= x1) fx = g(abs(xx - sx)) + g(xx + 1 + sx) + g(2 * W - 1 - sx - xx);
+        }
+        __syncwarp();
+        if (x0 + lane <= x1) {  // lane = window column; the window rows are independent read-modify-writes
+          float* c = tile + y0 * W + x0 + lane;
+          const int rows = y1 - y0 + 1;
+          float cv[kTaps];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) st[i] = __shfl_sync(0xffffffffu, c, i);
+          for (int dy = 0; dy < kTaps; ++dy)
+            if (dy < rows) cv[dy] = c[dy * W];
+#pragma unroll
+          for (int dy = 0; dy < kTaps; ++dy)
+            if (dy < rows) c[dy * W] = __fadd_rn(cv[dy], __fmul_rn(ws.fac[dy], fx));
+        }
+        __syncwarp();
+      }
+      // first arg max over the rows of the search box
+      for (int i = sy0 * (W / 4) + lane; i < (sy1 + 1) * (W / 4); i += 32) {
+        const float4 c = t4[i];
+        if (c.x > best) { best = c.x; best_i = 4 * i; }
+        if (c.y > best) { best = c.y; best_i = 4 * i + 1; }
+        if (c.z > best) { best = c.z; best_i = 4 * i + 2; }
+        if (c.w > best) { best = c.w; best_i = 4 * i + 3; }
+      }
+      warp_first_max(best, best_i);
+      if (best > 0.f) {
+        const int ys = best_i / W, xs = best_i % W;
+        if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {  // the stencil straight out of the tile: the same sums in the same order
+          st_c = tile[best_i]; st_l = tile[best_i - 1]; st_r = tile[best_i + 1]; st_u = tile[best_i - W]; st_d = tile[best_i + W];
           have_stencil = true;
         }
       }
-    } else {
-      have_stencil = tile_search<H, W>(ws, sp, sy0, sy1, tiles, tile_mask, best, best_i, st);
     }
-    PP_T(t_b2);
-    PP_TADD(6, t_b1, t_b2);
     if (!(best > 0.f)) best_i = 0;  // weights underflowed: C == 0 everywhere, first maximum is pixel 0
     const int ys = best_i / W, xs = best_i % W;
     lx = (float)xs; ly = (float)ys;
-    if (have_stencil && xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) subpixel(st[0], st[1], st[2], st[3], st[4], lx, ly);
+    if (xs > 0 && xs < W - 1 && ys > 0 && ys < H - 1) {
+      if (!have_stencil) {
+        // lanes 0..4: centre, left, right, up, down
+        const int ddx = lane == 1 ? -1 : (lane == 2 ? 1 : 0), ddy = lane == 3 ? -1 : (lane == 4 ? 1 : 0);
+        const float v = eval_c(ys + ddy, xs + ddx);
+        st_c = __shfl_sync(0xffffffffu, v, 0); st_l = __shfl_sync(0xffffffffu, v, 1); st_r = __shfl_sync(0xffffffffu, v, 2);
+        st_u = __shfl_sync(0xffffffffu, v, 3); st_d = __shfl_sync(0xffffffffu, v, 4);
+      }
+      subpixel(st_c, st_l, st_r, st_u, st_d, lx, ly);
+    }
     // conf = merged heatmap at the integer peak (one entry per pixel after the merge)
     const int pyx = (ys << 8) | xs;
     float cv = 0.f;
@@ -941,115 +760,41 @@ __device__ __forceinline__ bool decode_sparse(const DecodeParams& p, int item, W
     rec[2] = conf;
   }
   if (lane >= 4 && lane < 8) write_scalars(p, b, k, kf, lane - 4);
-  PP_T(t_c);
-  PP_TADD(7, t_a2, t_c);
-  PP_TADD(0, 0, 1);
   return true;
 }
 
-struct __align__(128) DecodeSmem {
-  float stage[kStages][64 * 48];  // the ring; dense path (after the ring has drained): P, row-convolved, C = stages 0..2
-  float tile[kTiles][64 * 48];    // scatter tiles
-  WarpList warp[kConsumers];
-  uint64_t full[kFullBars], empty[kStages];
+struct __align__(16) DecodeSmem {
+  float planes[kDecWarps * 64 * 48];  // sparse path: one scatter tile per warp; dense path: P, row-convolved, C
+  WarpList warp[kDecWarps];
   float red_f[2][kDenseWarps][4];
   int red_i[2][kDenseWarps][4];
-  unsigned short queue[kQueueCap];  // maps of this CTA (relative index) the sparse path declined
+  int queue[kDecWarps];
   int q_count;
-  int next_item;
-  unsigned tile_mask;  // free scatter tiles
 };
-static_assert(sizeof(DecodeSmem) <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
-static_assert(kFullBars >= 2 * kConsumers + kStages, "see the comment on the landed barriers");
 
-// Persistent CTA: warp kConsumers = producer (bulk copies into the ring), warps 0 .. kConsumers-1 = consumers
-// (one map each at a time, claimed in ring order); maps the sparse path declines are decoded afterwards by
-// warps 0 .. kDenseWarps-1 together.
-//
-// Barriers.  empty[s]: the producer is its only waiter and walks the ring in order - plain phase parity.  The "landed"
-// barriers are indexed by COPY NUMBER (n mod kFullBars), not by stage: maps are claimed in ring order but finish out
-// of order, so a consumer may start waiting for copy n while an earlier use of the same stage has not even been issued,
-// and a parity wait can only tell a barrier's current phase from the one before it.  Copy n - kFullBars must have
-// landed before anybody waits for copy n: otherwise no copy >= n - kFullBars + kStages has been issued (the ring is
-// in order), and each of the (kFullBars - kStages) / 2 >= kConsumers maps claimed in between would be pinning one
-// consumer warp in its wait - more warps than there are.
+// One warp per map, kDecWarps consecutive maps per CTA, kDecCtasPerSm CTAs per SM: 296 CTA slots on 148 SMs, so the
+// 544 CTAs of a batch-256 call run in 1.84 waves; maps the sparse path declines are decoded afterwards by the CTA.
 template <int H, int W, bool LOGITS>
-__global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const __grid_constant__ DecodeParams p) {
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_kernel(const __grid_constant__ DecodeParams p) {
   constexpr int NPX = H * W;
-  constexpr uint32_t MAP_BYTES = NPX * sizeof(float);
-  static_assert(NPX == 64 * 48, "stages are sized for 64 x 48 maps");
-  extern __shared__ __align__(128) uint8_t dec_smem_raw[];
+  static_assert(NPX == 64 * 48, "planes are sized for 64 x 48 maps");
+  extern __shared__ __align__(16) uint8_t dec_smem_raw[];
   DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(dec_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool tta = p.maps_flip != nullptr;
-  const int L = tta ? 2 : 1;  // stages per map
-  const int K = p.num_kpts;
-  const int i0 = blockIdx.x * p.items_per_cta;
-  const int n_items = max(0, min(p.count, i0 + p.items_per_cta) - i0);
   pdl_launch_dependents();
-  if (threadIdx.x < kFullBars) ptx::mbar_init(&sm.full[threadIdx.x], 1);
-  if (threadIdx.x < kStages) ptx::mbar_init(&sm.empty[threadIdx.x], 1);
-  if (threadIdx.x == 0) {
-    sm.q_count = 0;
-    sm.next_item = 0;
-    sm.tile_mask = (1u << kTiles) - 1u;
-  }
-  ptx::fence_barrier_init();
+  if (threadIdx.x == 0) sm.q_count = 0;
   __syncthreads();
   pdl_wait();  // the logits / scalars come from the previous kernels of the stream
-
-  if (warp == kConsumers) {
-    if (lane == 0) {
-      const int loads = n_items * L;
-      for (int n = 0; n < loads; ++n) {
-        const int s = n % kStages;
-        if (n >= kStages) ptx::mbar_wait(&sm.empty[s], ((n / kStages) & 1) ^ 1);  // the stage's previous map is done with it
-        const int item = i0 + (tta ? n >> 1 : n);
-        const float* src;
-        if (tta && (n & 1)) {
-          const int b = item / K, k = item % K;
-          src = p.maps_flip + (size_t)(b * K + p.flip_idx[k]) * NPX;
-        } else {
-          src = p.maps + (size_t)item * NPX;
-        }
-        uint64_t* bar = &sm.full[n % kFullBars];
-        ptx::mbar_arrive_expect_tx(bar, MAP_BYTES);
-        bulk_load(sm.stage[s], src, MAP_BYTES, bar);
-      }
-    }
-  } else {
-    WarpList& ws = sm.warp[warp];
-    for (;;) {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(&sm.next_item, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= n_items) break;
-      const int n0 = t * L;
-      const int s1 = n0 % kStages, s2 = (n0 + 1) % kStages;
-      PP_T(t_w0);
-      ptx::mbar_wait(&sm.full[n0 % kFullBars], (n0 / kFullBars) & 1);
-      if (tta) ptx::mbar_wait(&sm.full[(n0 + 1) % kFullBars], ((n0 + 1) / kFullBars) & 1);
-      PP_T(t_w1);
-      PP_TADD(1, t_w0, t_w1);
-      auto release = [&](int which) {
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&sm.empty[which ? s2 : s1]);
-      };
-      if (p.probe == 1) {
-        release(0);
-        if (tta) release(1);
-        continue;
-      }
-      if (!decode_sparse<H, W, LOGITS>(p, i0 + t, ws, lane, sm.stage[s1], sm.stage[s2], &sm.tile[0][0], &sm.tile_mask, release)) {
-        if (lane == 0) sm.queue[atomicAdd(&sm.q_count, 1)] = (unsigned short)t;
-      }
+  const int item = blockIdx.x * kDecWarps + warp;
+  if (item < p.count) {
+    if (!decode_sparse<H, W, LOGITS>(p, item, sm.warp[warp], lane, sm.planes + warp * NPX)) {
+      if (lane == 0) sm.queue[atomicAdd(&sm.q_count, 1)] = item;
     }
   }
-  __syncthreads();  // every map has been claimed and finished: all bulk copies have landed, the ring is free
+  __syncthreads();
   const int nq = sm.q_count;
-  if (nq == 0 || warp >= kDenseWarps) return;
   for (int q = 0; q < nq; ++q)
-    decode_dense<H, W>(p, i0 + sm.queue[q], sm.stage[0], sm.stage[1], sm.stage[2], sm.red_f, sm.red_i);
+    decode_dense<H, W>(p, sm.queue[q], sm.planes, sm.planes + NPX, sm.planes + 2 * NPX, sm.red_f, sm.red_i);
 }
 
 // 1-D factor of the reference's OKS kernel (post_processing.py:13-39), computed in double.
@@ -1074,19 +819,6 @@ static void fill_oks_taps(DecodeParams& p, int K, int H, int W) {
 }
 
 }  // namespace pp
-
-#ifdef PP_DECODE_TIMING
-extern "C" __attribute__((visibility("default"))) int pp_debug_decode_timing(unsigned long long* out8, int reset) {
-  using namespace pp;
-  PP_CHECK_CUDA(cudaDeviceSynchronize());
-  PP_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_dec_timing, sizeof(g_dec_timing)));
-  if (reset) {
-    unsigned long long z[8] = {};
-    PP_CHECK_CUDA(cudaMemcpyToSymbol(g_dec_timing, z, sizeof(z)));
-  }
-  return PP_OK;
-}
-#endif
 
 extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const float* maps_flip,
                          const int32_t* flip_indices, const float* scalars, const float* scalars_flip,
@@ -1133,21 +865,15 @@ extern "C" int pp_decode(const pp_decode_cfg* cfg, const float* maps, const floa
   const int64_t count = (int64_t)batch * cfg->num_keypoints;
   PP_REQUIRE(count < (1ll << 31), PP_ERR_INVALID, "pp_decode: batch too large");
   p.count = (int)count;
-  PP_REQUIRE((reinterpret_cast<uintptr_t>(maps) & 15) == 0 && (reinterpret_cast<uintptr_t>(maps_flip) & 15) == 0, PP_ERR_INVALID,
-             "pp_decode: maps / maps_flip must be 16-byte aligned (bulk copies into shared memory)");
   static PerDeviceOnce attr_set;
   auto kern = cfg->input_is_logits ? decode_kernel<64, 48, true> : decode_kernel<64, 48, false>;
-  if (attr_set.first()) {  // one persistent CTA per SM with the whole 227 KB of shared memory
+  if (attr_set.first()) {  // shared memory for kDecCtasPerSm CTAs per SM (about 110 KB each)
     PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
     PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PP_CHECK_CUDA(cudaFuncSetAttribute(decode_kernel<64, 48, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
-  // contiguous ranges of maps, one CTA per SM (more CTAs only when a range would exceed the dense-path queue)
-  const int sms = device_sm_count();
-  int64_t ctas = count < sms ? count : sms;
-  if ((count + ctas - 1) / ctas > kQueueCap) ctas = (count + kQueueCap - 1) / kQueueCap;
-  p.items_per_cta = (int)((count + ctas - 1) / ctas);
-  p.probe = getenv("PP_DECODE_PROBE") ? atoi(getenv("PP_DECODE_PROBE")) : 0;
-  const int grid = (int)((count + p.items_per_cta - 1) / p.items_per_cta);
+  const int grid = (int)((count + kDecWarps - 1) / kDecWarps);
   PP_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kDecThreads), sizeof(DecodeSmem), (cudaStream_t)stream, p));
   count_launch();
   PP_CHECK_CUDA(cudaGetLastError());
