@@ -208,8 +208,8 @@ PP_API int pp_revert_heatmaps(const float* heatmaps, const double* warp_mats, in
  *  impl     0 = default (tcgen05: S and P.V on the 5th-gen tensor cores, P kept in TMEM),
  *           1 = mma.sync kernel, 2 = tcgen05 kernel (tests compare the two)
  * Built for tokens == 192 and head_dim 32 / 64; tensor-core precisions only.  The tcgen05 kernel runs persistent CTAs
- * that take (image, head) units from a device-side counter (64 rotating slots, re-armed by each launch's last CTA):
- * launches may overlap on different streams as long as fewer than 64 of them are in flight at once.
+ * on a static schedule (no device-global scheduler state): launches may overlap freely on different streams and
+ * replay from CUDA graphs.
  * ---------------------------------------------------------------------------------- */
 PP_API int pp_attention(int32_t precision, const void* qkv_op, int32_t batch, int32_t tokens, int32_t heads,
                         int32_t head_dim, void* out_op, int32_t impl, void* stream);
@@ -321,6 +321,21 @@ typedef struct pp_profile {
 } pp_profile;
 PP_API int pp_engine_profile_begin(pp_engine* e);
 PP_API int pp_engine_profile_end(pp_engine* e, pp_profile* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU: persons are independent, so every rank runs pp_engine_infer on its
+ * contiguous shard of the crops and the ONLY exchange is one all-gather of the decoded records.
+ * Replaces mmengine's end-of-epoch `collect_results` (pickled python objects through
+ * torch.distributed, reached from tools/test.py:136 -> mmengine Evaluator) for this path.
+ *  nccl_comm        the caller's ncclComm_t (torch.distributed: ProcessGroupNCCL._comm_ptr()); the library
+ *                   resolves ncclAllGather from the libnccl already loaded in the process - it does not link NCCL
+ *  send             device fp32, this rank's records (B_local, K, 7) - pass the buffer pp_engine_infer / pp_decode
+ *                   wrote (`records`), no staging copy in between
+ *  recv             device fp32 (world * B_local, K, 7), rank order = person order for equal contiguous shards
+ *  floats_per_rank  B_local * K * 7
+ * One ncclAllGather on `stream`; PP_ERR_UNSUPPORTED when no NCCL library is loaded in the process.
+ * ---------------------------------------------------------------------------------- */
+PP_API int pp_allgather(void* nccl_comm, const float* send, float* recv, int64_t floats_per_rank, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libprobpose_b200.so")
-SOURCES = ["capi.cu", "decode.cu", "decode_udp.cu", "gemm.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "vit_ops.cu", "head_ops.cu", "crop.cu", "revert.cu", "engine.cu"]
+SOURCES = ["capi.cu", "decode.cu", "decode_udp.cu", "gemm.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "vit_ops.cu", "head_ops.cu", "crop.cu", "revert.cu", "collective.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out.strip():
             print(out)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -77,6 +77,7 @@ class TopdownPoseEstimator(nn.Module):
             self.head = MODELS.build(head)
             self.head.test_cfg = self.test_cfg.copy()
         self._fused = None
+        self._stage = None  # (pinned host crops, device crops, pinned host records) of the fused path, grown on demand
         self.eval()
 
     with_neck = property(lambda self: hasattr(self, "neck") and self.neck is not None)
@@ -106,14 +107,62 @@ class TopdownPoseEstimator(nn.Module):
     def _device(self):
         return self.backbone.pos_embed.device
 
+    def _staging(self, batch: int, shape, rec_shape, device):
+        """Pinned host staging for the step's crops and records plus the device-side crop buffer (one allocation per
+        capacity, reused by every call): per-person host tensors are gathered straight into pinned memory (no
+        ``torch.stack`` into pageable memory followed by a staged pageable copy), go to the device with ONE asynchronous
+        copy, and the records come back through pinned memory as well."""
+        st = self._stage
+        if st is None or st[0].shape[0] < batch or tuple(st[0].shape[1:]) != tuple(shape) or st[1].device != device \
+                or tuple(st[2].shape[1:]) != tuple(rec_shape):
+            cap = max(16, 1 << (max(batch, 1) - 1).bit_length())
+            st = (torch.empty((cap, *shape), dtype=torch.uint8).pin_memory(),
+                  torch.empty((cap, *shape), dtype=torch.uint8, device=device),
+                  torch.empty((cap, *rec_shape), dtype=torch.float32).pin_memory())
+            self._stage = st
+        return st
+
+    def _upload(self, inputs, device) -> Optional[torch.Tensor]:
+        """uint8 crops on the host (a list of per-person (3, H, W) tensors as mmengine's ``pseudo_collate`` hands them
+        over, or one stacked tensor) -> device tensor through the pinned staging buffer.  Returns None when the inputs
+        are not host uint8 crops (the caller takes the generic route)."""
+        if isinstance(inputs, torch.Tensor):
+            if inputs.is_cuda or inputs.dtype != torch.uint8 or inputs.dim() != 4:
+                return None
+            n, shape = inputs.shape[0], inputs.shape[1:]
+            if inputs.is_pinned():  # already page-locked: copy straight from the caller's buffer
+                _, dev_buf, _ = self._staging(n, shape, self._rec_shape(), device)
+                dev_buf[:n].copy_(inputs, non_blocking=True)
+                return dev_buf[:n]
+            host, dev_buf, _ = self._staging(n, shape, self._rec_shape(), device)
+            host[:n].copy_(inputs)
+        else:
+            inputs = list(inputs)
+            if not inputs or any((not isinstance(t, torch.Tensor)) or t.is_cuda or t.dtype != torch.uint8 or t.dim() != 3
+                                 for t in inputs):
+                return None
+            n, shape = len(inputs), inputs[0].shape
+            host, dev_buf, _ = self._staging(n, shape, self._rec_shape(), device)
+            for i, t in enumerate(inputs):
+                host[i].copy_(t)
+        dev_buf[:n].copy_(host[:n], non_blocking=True)
+        return dev_buf[:n]
+
+    def _rec_shape(self):
+        return (self.head.out_channels, 7 if isinstance(self.head, ProbMapHead) else 3)
+
     # ---- mmengine BaseModel surface -----------------------------------------------------
     @torch.no_grad()
     def test_step(self, data: dict) -> list:
         """``BaseModel.test_step``: ``data = dict(inputs=[uint8 BGR (3,H,W)...], data_samples=[...])``."""
-        inputs = PoseDataPreprocessor.stack(data["inputs"])
         pre = self.data_preprocessor
-        if (self._fusable() and inputs.dtype == torch.uint8 and getattr(pre, "channel_conversion", False)
-                and getattr(pre, "mean_std", None)):
+        fused = self._fusable() and getattr(pre, "channel_conversion", False) and getattr(pre, "mean_std", None)
+        if fused:
+            dev = self._upload(data["inputs"], self._device())  # host uint8 crops: pinned staging, one async copy
+            if dev is not None:
+                return self._predict_fused(dev, data["data_samples"], pinned_records=True)
+        inputs = PoseDataPreprocessor.stack(data["inputs"])
+        if fused and inputs.dtype == torch.uint8:
             return self._predict_fused(inputs.to(self._device(), non_blocking=True).contiguous(), data["data_samples"])
         data = pre(data, False)
         return self.forward(data["inputs"], data["data_samples"], mode="predict")
@@ -165,8 +214,9 @@ class TopdownPoseEstimator(nn.Module):
             batch_pred_instances, batch_pred_fields = preds, None
         return self.add_pred_to_datasample(batch_pred_instances, batch_pred_fields, data_samples)
 
-    def _predict_fused(self, inputs: torch.Tensor, data_samples: list) -> list:
-        """One ``pp_engine_infer`` call for the batch (uint8 BGR or normalised fp32 crops)."""
+    def _predict_fused(self, inputs: torch.Tensor, data_samples: list, pinned_records: bool = False) -> list:
+        """One ``pp_engine_infer`` call for the batch (uint8 BGR or normalised fp32 crops).  ``pinned_records``: read
+        the records back through the pinned staging buffer (asynchronous copy + one stream synchronisation)."""
         cfg = self.test_cfg
         flip = bool(cfg.get("flip_test", False))
         want_hm = bool(cfg.get("output_heatmaps", False))
@@ -174,6 +224,11 @@ class TopdownPoseEstimator(nn.Module):
         eng = self._fused_engine(inputs.shape[0] * (2 if flip else 1), inputs.device)
         out = eng.infer(inputs, flip_test=flip, flip_indices=flip_indices, return_heatmaps=want_hm)
         records, heatmaps = out if want_hm else (out, None)
+        if pinned_records and self._stage is not None and self._stage[2].shape[0] >= records.shape[0]:
+            host = self._stage[2][:records.shape[0]]
+            host.copy_(records, non_blocking=True)
+            torch.cuda.current_stream(records.device).synchronize()
+            records = host
         fields = [PixelData(heatmaps=hm) for hm in heatmaps] if want_hm else None
         if cfg.get("output_keypoint_indices", None) is not None:
             return self.add_pred_to_datasample(self.head.pack_records(records), fields, data_samples)

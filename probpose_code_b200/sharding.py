@@ -5,7 +5,7 @@ mmengine's pickled ``collect_results``).  Works with any ``torch.distributed`` b
 the GPUs, gloo in the CPU tests."""
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -38,3 +38,74 @@ def gather_records(local: torch.Tensor, n_total: int, group=None) -> torch.Tenso
     if all(s == cap for s in sizes):
         return out
     return torch.cat([out[r * cap: r * cap + sizes[r]] for r in range(world)], 0)
+
+
+def nccl_comm_ptr(device: torch.device, group=None) -> int:
+    """The ncclComm_t of torch.distributed's NCCL process group for `device` (``ProcessGroupNCCL._comm_ptr()``), for
+    ``pp_allgather``.  The communicator must exist: call after ``init_process_group(..., device_id=device)`` or after
+    a first collective."""
+    pg = group if group is not None else dist.distributed_c10d._get_default_group()
+    backend = pg._get_backend(torch.device(device))
+    ptr = backend._comm_ptr()
+    if not ptr:
+        raise RuntimeError("the NCCL communicator of this process group is not initialised yet")
+    return int(ptr)
+
+
+class RecordGatherer:
+    """The per-step all-gather of the decoded records, off the compute stream.
+
+    Two send buffers (the decode kernel writes its records straight into ``send_buffer(i)``) and two receive buffers,
+    allocated once; ``gather(i)`` enqueues ``pp_allgather`` (one ``ncclAllGather`` behind the C ABI) on a side stream
+    that waits for step i's decode, so the collective of step i runs under the kernels of step i + 1; the compute
+    stream only waits for a buffer's previous gather before the decode of step i + 2 overwrites it."""
+
+    def __init__(self, batch_local: int, world: int, device, keypoints: int = 17, floats: int = 7, group=None):
+        from ._lib import lib  # noqa: F401  (fails loudly if the library is missing)
+        self.device = torch.device(device)
+        self.world, self.batch = world, batch_local
+        self.count = batch_local * keypoints * floats
+        self.send = [torch.empty((batch_local, keypoints, floats), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.recv = [torch.empty((world * batch_local, keypoints, floats), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.stream = torch.cuda.Stream(self.device)
+        self.decoded = [torch.cuda.Event() for _ in range(2)]
+        self.t0 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        self.t1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        self.pending = [False, False]
+        self.comm = nccl_comm_ptr(self.device, group)
+        self._ms, self._n = 0.0, 0
+
+    def send_buffer(self, i: int) -> torch.Tensor:
+        j = i & 1
+        if self.pending[j]:  # step i - 2's gather still reads this buffer
+            torch.cuda.current_stream(self.device).wait_event(self.t1[j])
+        return self.send[j]
+
+    def gather(self, i: int) -> torch.Tensor:
+        """Enqueue the all-gather of ``send_buffer(i)`` (written on the current stream); returns the receive buffer,
+        valid after :meth:`wait` (or after the side stream reaches this point)."""
+        from ._lib import check, lib
+        j = i & 1
+        if self.pending[j]:
+            self._ms += self.t0[j].elapsed_time(self.t1[j]) if self.t1[j].query() else 0.0
+            self._n += 1 if self.t1[j].query() else 0
+        self.decoded[j].record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.decoded[j])
+            self.t0[j].record(self.stream)
+            check(lib().pp_allgather(self.comm, self.send[j].data_ptr(), self.recv[j].data_ptr(), self.count,
+                                     self.stream.cuda_stream), "pp_allgather")
+            self.t1[j].record(self.stream)
+        self.pending[j] = True
+        return self.recv[j]
+
+    def wait(self) -> None:
+        """The current stream waits for every outstanding gather."""
+        cur = torch.cuda.current_stream(self.device)
+        for j in range(2):
+            if self.pending[j]:
+                cur.wait_event(self.t1[j])
+
+    def gather_ms(self) -> Optional[float]:
+        """Mean device time of a gather (side-stream events), over the gathers whose buffers have been reused."""
+        return self._ms / self._n if self._n else None
