@@ -323,6 +323,16 @@ PP_API int pp_engine_profile_begin(pp_engine* e);
 PP_API int pp_engine_profile_end(pp_engine* e, pp_profile* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Operand range guard.  fp16 operands clamp at +-65504 - in PP_PREC_FP16X3 that is |activation| > 1023.5 after the
+ * 64x operand scale (trained ViTs have massive-activation channels; a clamp would be silently wrong keypoints).
+ * Every kernel that writes an operand raises a sticky device flag when it clamps a value.  This call synchronises
+ * the CURRENT device, returns in *flagged how many kernel groups clamped since the last clear (0 = none) and,
+ * with clear != 0, re-arms the flags.  The Python layer checks it after the first call of an engine and
+ * periodically, and raises: switch the model to precision "fp32_simt" (no operand range limit).
+ * ---------------------------------------------------------------------------------- */
+PP_API int pp_operand_overflow(int32_t clear, int32_t* flagged);
+
+/* ------------------------------------------------------------------------------------
  * Multi-GPU: persons are independent, so every rank runs pp_engine_infer on its
  * contiguous shard of the crops and the ONLY exchange is one all-gather of the decoded records.
  * Replaces mmengine's end-of-epoch `collect_results` (pickled python objects through

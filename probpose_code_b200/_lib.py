@@ -24,7 +24,7 @@ EXPORTS = [
     "pp_engine_workspace_bytes", "pp_engine_create", "pp_engine_destroy", "pp_engine_load", "pp_engine_finalize",
     "pp_engine_backbone", "pp_engine_head", "pp_engine_infer", "pp_engine_last_launch_count",
     "pp_engine_profile_begin", "pp_engine_profile_end", "pp_engine_set_graph", "pp_engine_graph_replay_count", "pp_crop_warp", "pp_attention", "pp_decode_udp", "pp_revert_heatmaps",
-    "pp_allgather",
+    "pp_allgather", "pp_operand_overflow",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "decode", "other")
 
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
                                      C.c_int32, C.c_void_p, C.c_void_p]
     l.pp_attention.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                C.c_void_p]
+    l.pp_operand_overflow.argtypes = [C.c_int32, C.POINTER(C.c_int32)]
     l.pp_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     if True:
         l.pp_engine_workspace_bytes.restype = C.c_size_t

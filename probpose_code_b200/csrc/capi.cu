@@ -3,6 +3,9 @@
 
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 namespace pp {
 
 static thread_local char g_error[1024] = "";
@@ -30,6 +33,22 @@ int device_sm_count() {
   return n;
 }
 
+namespace {
+std::vector<OverflowReader>& overflow_readers() {
+  static std::vector<OverflowReader> v;
+  return v;
+}
+std::mutex& overflow_mutex() {
+  static std::mutex m;
+  return m;
+}
+}  // namespace
+
+void register_overflow_reader(OverflowReader fn) {
+  std::lock_guard<std::mutex> lk(overflow_mutex());
+  overflow_readers().push_back(fn);
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -41,6 +60,21 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* pp_last_error(void) { return pp::g_error; }
 extern "C" const char* pp_version(void) { return "probpose_b200 0.1.0 sm_100a"; }
+
+extern "C" int pp_operand_overflow(int32_t clear, int32_t* flagged) {
+  using namespace pp;
+  PP_REQUIRE(flagged != nullptr, PP_ERR_INVALID, "pp_operand_overflow: flagged is NULL");
+  *flagged = 0;
+  PP_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(overflow_mutex());
+  for (OverflowReader fn : overflow_readers()) {
+    unsigned v = 0;
+    PP_REQUIRE(fn(clear, &v) == 0, PP_ERR_CUDA, "pp_operand_overflow: could not read a device flag: %s",
+               cudaGetErrorString(cudaGetLastError()));
+    *flagged += v ? 1 : 0;
+  }
+  return PP_OK;
+}
 
 extern "C" int pp_attention(int32_t precision, const void* qkv_op, int32_t batch, int32_t tokens, int32_t heads,
                             int32_t head_dim, void* out_op, int32_t impl, void* stream) {

@@ -118,7 +118,40 @@ constexpr float kAccScaleInv = 1.0f / 4096.0f;  // (A * 64) . (W * 64) -> A . W
 __host__ __device__ inline int operand_elem_bytes(int prec) { return prec == PP_PREC_FP32_SIMT ? 4 : 2; }
 __host__ __device__ inline int64_t operand_row_elems(int prec, int64_t k) { return prec == PP_PREC_FP16X3 ? 2 * k : k; }
 
+// ---- operand range guard -----------------------------------------------------------------
+// fp16 operands clamp at +-65504 (FP16X3: |a| > 1023.5 after the 64x operand scale).  A clamp is silent wrong
+// output, so every producer of an operand raises a sticky device flag when it clamps; pp_operand_overflow() reads
+// (and clears) it.  One flag per translation unit - the library is built without relocatable device code - each
+// registered with capi.cu at load time.
+static __device__ unsigned g_op_overflow;
+__device__ __forceinline__ void note_overflow(float v) {
+  if (fabsf(v) > 65504.0f) g_op_overflow = 1u;
+}
+__device__ __forceinline__ void note_overflow4(float a, float b, float c, float d) {
+  if (fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))) > 65504.0f) g_op_overflow = 1u;
+}
+typedef int (*OverflowReader)(int clear, unsigned* flagged);
+void register_overflow_reader(OverflowReader fn);  // capi.cu
+namespace {
+struct OverflowRegistration {
+  OverflowRegistration() {
+    register_overflow_reader([](int clear, unsigned* flagged) -> int {
+      unsigned v = 0;
+      if (cudaMemcpyFromSymbol(&v, g_op_overflow, sizeof(v)) != cudaSuccess) return 1;
+      if (v && clear) {
+        const unsigned zero = 0;
+        if (cudaMemcpyToSymbol(g_op_overflow, &zero, sizeof(zero)) != cudaSuccess) return 1;
+      }
+      *flagged = v;
+      return 0;
+    });
+  }
+};
+static OverflowRegistration overflow_registration_;
+}  // namespace
+
 __device__ __forceinline__ __half sat_half(float v) {
+  note_overflow(v);
   return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
 }
 

@@ -192,6 +192,7 @@ template <int PREC>
 __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int col, int k, float4 v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
     uint2 hi, lo;
+    note_overflow4(v.x, v.y, v.z, v.w);  // the conversion below clamps: never silently
     hi.x = pack_half2_sat(v.x, v.y); hi.y = pack_half2_sat(v.z, v.w);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
     float r0, r1, r2, r3;  // residues v - hi: exact, one packed subtraction per pair
@@ -210,6 +211,7 @@ __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + rowk + col) = o;
   } else {
     uint2 o;
+    note_overflow4(v.x, v.y, v.z, v.w);
     o.x = pack_half2_sat(v.x, v.y); o.y = pack_half2_sat(v.z, v.w);
     *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + rowk + col) = o;
   }

@@ -146,6 +146,21 @@ class Engine:
                                         None if merged is None else merged.data_ptr(), _stream()), "pp_engine_infer")
         return (rec, merged) if return_heatmaps else rec
 
+    def operand_overflow(self, clear: bool = True) -> bool:
+        """True when a kernel on this device clamped an fp16 operand (|activation| > 1023.5 in fp16x3) since the last
+        clear: the outputs computed meanwhile are not trustworthy (``pp_operand_overflow``; synchronises the device)."""
+        n = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(lib().pp_operand_overflow(int(clear), C.byref(n)), "pp_operand_overflow")
+        return n.value > 0
+
+    def raise_on_overflow(self) -> None:
+        if self.operand_overflow():
+            raise _lib.PPError(
+                f"an activation exceeded the operand range of precision {self.precision!r} (|a| > 1023.5 for fp16x3 / 65504 for "
+                "fp16) and was clamped: the results of this call are wrong. Build the model with precision='fp32_simt' "
+                "(no range limit) for this checkpoint")
+
     @property
     def last_launch_count(self) -> int:
         return int(lib().pp_engine_last_launch_count(self._h))

@@ -224,6 +224,12 @@ class TopdownPoseEstimator(nn.Module):
         eng = self._fused_engine(inputs.shape[0] * (2 if flip else 1), inputs.device)
         out = eng.infer(inputs, flip_test=flip, flip_indices=flip_indices, return_heatmaps=want_hm)
         records, heatmaps = out if want_hm else (out, None)
+        # operand range guard: after the first call of an engine (weights + a real batch have been seen) and every
+        # 256 calls afterwards - the check synchronises the device, so not on every call
+        self._calls = getattr(self, "_calls", 0) + 1
+        if getattr(self, "_guard_engine", None) is not eng or self._calls % 256 == 0:
+            eng.raise_on_overflow()
+            self._guard_engine = eng
         if pinned_records and self._stage is not None and self._stage[2].shape[0] >= records.shape[0]:
             host = self._stage[2][:records.shape[0]]
             host.copy_(records, non_blocking=True)

@@ -200,3 +200,27 @@ def test_parity_at_a_batch_that_fills_the_gpu(setup):
     for lo in range(0, n, 4):
         part = eng.infer(crops[lo:lo + 4].cuda().contiguous(), flip_test=True).cpu()
         assert torch.equal(part, rec[lo:lo + 4]), f"records of crops[{lo}:{lo + 4}] depend on the batch composition"
+
+
+def test_operand_range_guard(setup):
+    """fp16x3 operands clamp at |a| > 1023.5: a checkpoint whose activations get there must be flagged, never decoded
+    silently (pp_operand_overflow; the estimator raises after the first call of an engine)."""
+    import probpose_code_b200.mmpose_api as api
+    from probpose_code_b200 import _lib
+    eng = _engine("fp16x3", setup["sd"])
+    eng.operand_overflow()  # clear whatever earlier tests left behind
+    eng.infer(setup["crops"].cuda())
+    assert not eng.operand_overflow()
+    sd = dict(setup["sd"])
+    sd["backbone.layers.3.ln2.weight"] = sd["backbone.layers.3.ln2.weight"] * 3000.0  # LN output ~ 3000: beyond the range
+    bad = _engine("fp16x3", sd)
+    bad.infer(setup["crops"].cuda())
+    assert bad.operand_overflow() and not bad.operand_overflow()  # sticky until read, cleared by the read
+    model = api.MODELS.build(api.probpose_small_cfg(precision="fp16x3"))
+    model.load_state_dict(sd)
+    model.to("cuda:0")
+    with pytest.raises(_lib.PPError, match="operand range"):
+        model.test_step(dict(inputs=[c for c in setup["crops"]], data_samples=api.make_data_samples(3)))
+    ok = _engine("fp32_simt", sd)  # the CUDA-core path has no operand range limit
+    ok.infer(setup["crops"].cuda())
+    assert not ok.operand_overflow()
