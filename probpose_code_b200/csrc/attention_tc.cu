@@ -30,9 +30,6 @@
 #include "ptx.cuh"
 
 #include <math.h>
-#include <string.h>
-
-#include <type_traits>
 
 namespace pp {
 
@@ -75,30 +72,6 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-// TMEM load without the wait: the caller overlaps it with arithmetic and calls tmem_ld_wait() before using the values.
-__device__ __forceinline__ void tmem_ld_x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Barrier wait of the 256 softmax threads: back off between polls so that the waiting CTA does not take
 // issue slots from the CTA that shares the SM (bounded like ptx::mbar_wait: a lost arrival traps).
@@ -439,366 +412,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
 }
 
-// =================================================================================================
-// Warp-specialised kernel (head width 32): ONE persistent CTA per SM, 10 warps
-//   warps 0, 1  slot drivers   one thread each, does no softmax: TMA loads (Q / K and V of the slot's next unit as soon as
-//                              the slot's MMAs have released them) and the MMAs S = Q K^T, O = P V of its slot
-//   warps 2-9   softmax group 0   two threads per query row (TMEM lane): warps w and w + 4 of a group may access the same
-//   warps 10-17 softmax group 1   lane quarter and split the row's 192 keys in halves (row max / sum meet in shared memory)
-// Two SLOTS (shared memory 80 KB + TMEM 256 columns each: S / P 192, O 32) hold two (image, head) units at a time; slot g
-// belongs to softmax group g.  While group 0 runs its exp pass the tensor pipe serves group 1 and vice versa, and the
-// softmax warps never issue an MMA or a load.  Per slot and tile:
-//   qk_full -> [MMA] S -> s_full -> [group] max, then per 32-key chunk: exp, P chunk -> p_chunk[c] -> [MMA] the two
-//   k-steps of P V for that chunk, under the group's exp pass of the following chunks (fixed chunk order: deterministic
-//   accumulation); after the last chunk the next S at once (MMAs of one thread execute in order) -> o_full ->
-//   [group] O / rowsum -> global, o_empty -> [MMA] may overwrite O.
-// =================================================================================================
-constexpr int kWsThreads = 576;  // 2 slot drivers + 2 softmax groups of 8 warps
-
-template <int DH, int SPLIT>
-struct WsCfg {
-  static constexpr int NOPS = SPLIT == 3 ? 2 : 1;
-  static constexpr int ROWB = DH * 2;
-  static constexpr int Q_BYTES = 128 * ROWB;     // one Q tile, one plane
-  static constexpr int KV_BYTES = kNTok * ROWB;  // K or V, one plane
-  static constexpr int OFF_K = 2 * NOPS * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + NOPS * KV_BYTES;
-  static constexpr int SLOT_BYTES = OFF_V + NOPS * KV_BYTES;
-  static constexpr int OFF_BAR = 2 * SLOT_BYTES;
-  static constexpr int OFF_X = OFF_BAR + 512;                // row max / row sum halves: float [2 groups][2][2 halves][128]
-  static constexpr int SMEM_BYTES = OFF_X + 2 * 2 * 2 * 128 * 4 + 1024;  // + alignment slack
-  static constexpr int LOAD_QK_BYTES = NOPS * (2 * Q_BYTES + KV_BYTES);
-  static constexpr int LOAD_V_BYTES = NOPS * KV_BYTES;
-  static constexpr int SLOT_COLS = 256;  // S / P: 192 columns, O: 2 DH columns at 192 ([P V_hi | P_hi V_lo] in FP16X3)
-  static_assert(DH == 32, "two slots of Q / K / V fit the shared memory at head width 32 only (and the read-out splits 32 columns in two sectors)");
-  static_assert(SLOT_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
-};
-
-// kPChunk + 6 g + c: P of 32-key chunk c of slot g's current tile is in TMEM (4 arrivals: one per softmax warp)
-enum WsBar { kQkFull = 0, kVFull = 2, kQkEmpty = 4, kVEmpty = 6, kSFull = 8, kOFull = 10, kOEmpty = 12, kPChunk = 14, kWsBars = 26 };
-
-template <int DH, int SPLIT, bool BF16>
-__global__ void __launch_bounds__(kWsThreads, 1)
-attention_ws_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const int heads,
-                    const int units, uint16_t* __restrict__ out_op, long long* __restrict__ trace) {
-  using Cfg = WsCfg<DH, SPLIT>;
-  constexpr int NOPS = Cfg::NOPS, ROWB = Cfg::ROWB;
-  extern __shared__ uint8_t att_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kWsBars);
-
-  pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = heads * DH;
-  // this CTA's units: blockIdx.x + j * gridDim.x; unit j lives in slot j & 1
-  const int n_mine = units > (int)blockIdx.x ? (units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int n_slot[2] = {(n_mine + 1) >> 1, n_mine >> 1};
-
-  if (threadIdx.x == 0) {
-    ptx::prefetch_tensormap(&tm_q);
-    ptx::prefetch_tensormap(&tm_kv);
-    for (int i = 0; i < kWsBars; ++i) ptx::mbar_init(&bars[i], i >= kPChunk ? 4 : (i >= kOEmpty ? 8 : 1));
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tcgen05_fence_before();
-  __syncthreads();
-  ptx::tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();  // qkv comes from the qkv GEMM; out_op is still read by it
-
-  auto slot_smem = [&](int g) { return smem + g * Cfg::SLOT_BYTES; };
-
-  if (warp < 2) {
-    // ------------------------------------------------------------------ slot driver: TMA + MMA of slot `warp`
-    // One thread per slot, blocking barrier waits (the hardware parks the thread): it shares its scheduler with two
-    // softmax warps, and a polling loop over both slots was measured to take ~500 cycles per step - the group waited
-    // 5 000 cycles for a P V that executes in 150.
-    auto drive = [&](auto slot_c) {
-      constexpr int g = decltype(slot_c)::value;  // compile-time slot: every address below is a uniform-datapath value
-      if (n_slot[g] <= 0) return;
-      uint8_t* sb = slot_smem(g);
-      constexpr uint32_t idesc_s = ptx::make_idesc_f16(BF16, 128, kNTok);
-      constexpr uint32_t idesc_o = ptx::make_idesc_f16(BF16, 128, DH) | (1u << 16);  // B (= V, keys x d_h) is MN-major
-      constexpr int NCHK = kNTok / 32;
-      const uint32_t t_s = tmem_base + g * Cfg::SLOT_COLS, t_o = t_s + 192;
-      const uint32_t q0h = ptx::kmajor_desc_lo(ptx::smem_u32(sb)), q1h = ptx::kmajor_desc_lo(ptx::smem_u32(sb + NOPS * Cfg::Q_BYTES));
-      const uint32_t kh = ptx::kmajor_desc_lo(ptx::smem_u32(sb + Cfg::OFF_K)), vh = ptx::kmajor_desc_lo(ptx::smem_u32(sb + Cfg::OFF_V));
-      constexpr uint32_t QLO = Cfg::Q_BYTES >> 4, KVLO = Cfg::KV_BYTES >> 4, KSTEP = (16 * ROWB) >> 4;
-      auto load_qk = [&](int i) {
-        const int unit = (int)blockIdx.x + (2 * i + g) * (int)gridDim.x;
-        const int row0 = (unit / heads) * kNTok, hc = (unit % heads) * DH;
-        ptx::mbar_arrive_expect_tx(&bars[kQkFull + g], Cfg::LOAD_QK_BYTES);
-#pragma unroll
-        for (int part = 0; part < NOPS; ++part) {
-          const int c = part * 3 * D + hc;  // q | k | v column blocks, lo plane 3 D further
-          ptx::tma_load_2d(sb + part * Cfg::Q_BYTES, &tm_q, &bars[kQkFull + g], c, row0);
-          ptx::tma_load_2d(sb + Cfg::OFF_K + part * Cfg::KV_BYTES, &tm_kv, &bars[kQkFull + g], c + D, row0);
-          // rows 192.. of the second tile belong to the next image (or are zero-filled): never stored
-          ptx::tma_load_2d(sb + (NOPS + part) * Cfg::Q_BYTES, &tm_q, &bars[kQkFull + g], c, row0 + 128);
-        }
-      };
-      auto load_v = [&](int i) {
-        const int unit = (int)blockIdx.x + (2 * i + g) * (int)gridDim.x;
-        const int row0 = (unit / heads) * kNTok, hc = (unit % heads) * DH;
-        ptx::mbar_arrive_expect_tx(&bars[kVFull + g], Cfg::LOAD_V_BYTES);
-#pragma unroll
-        for (int part = 0; part < NOPS; ++part)
-          ptx::tma_load_2d(sb + Cfg::OFF_V + part * Cfg::KV_BYTES, &tm_kv, &bars[kVFull + g], part * 3 * D + hc + 2 * D, row0);
-      };
-      auto issue_s = [&](int tile) {  // S = Q K^T for one query tile
-        const uint32_t qh = tile ? q1h : q0h;
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint64_t da = ptx::kmajor_desc<ROWB>(qh + 2 * kk), db = ptx::kmajor_desc<ROWB>(kh + 2 * kk);
-          ptx::umma_f16(t_s, da, db, idesc_s, kk != 0 ? 1u : 0u);
-          if constexpr (SPLIT == 3) {
-            ptx::umma_f16(t_s, da, ptx::kmajor_desc<ROWB>(kh + KVLO + 2 * kk), idesc_s, 1u);
-            ptx::umma_f16(t_s, ptx::kmajor_desc<ROWB>(qh + QLO + 2 * kk), db, idesc_s, 1u);
-          }
-        }
-        ptx::umma_commit(&bars[kSFull + g]);
-      };
-      // O (+)= P V for the 32 keys of chunk c (P: [hi : 16 columns | lo : 16 columns]).  An MMA of this size costs ~90
-      // cycles whatever its N (measured: the tensor pipe, not the softmax, bounds the kernel), so the split product
-      // uses TWO instructions per 16-key step instead of three: P_hi x [V_hi | V_lo] as ONE N = 2 d_h MMA - V is an
-      // MN-major operand, and its leading-dimension byte offset (the stride between 64-byte column atoms) is set to
-      // the distance between the hi and lo planes, so columns d_h.. of "B" are V_lo - plus P_lo x V_hi (N = d_h) into
-      // the first d_h columns.  The read-out adds the two column blocks.
-      constexpr uint32_t idesc_o2 = ptx::make_idesc_f16(BF16, 128, 2 * DH) | (1u << 16);
-      auto v_desc = [&](int j, bool both) -> uint64_t {
-        const uint32_t lo = ((vh + KSTEP * j) & 0x3fffu) | ((both ? KVLO : 1u) << 16);
-        return ptx::kmajor_desc<ROWB>(lo) ;
-      };
-      auto issue_o_chunk = [&](int c) {
-#pragma unroll
-        for (int j = 2 * c; j < 2 * c + 2; ++j) {
-          const uint32_t a_hi = t_s + 32 * c + 8 * (j & 1);
-          if constexpr (SPLIT == 3) {
-            umma_f16_ts(t_o, a_hi, v_desc(j, true), idesc_o2, j != 0 ? 1u : 0u);
-            umma_f16_ts(t_o, a_hi + 16, v_desc(j, false), idesc_o, 1u);
-          } else {
-            umma_f16_ts(t_o, a_hi, v_desc(j, false), idesc_o, j != 0 ? 1u : 0u);
-          }
-        }
-      };
-      const int n = n_slot[g];
-      load_qk(0);
-      load_v(0);
-      ptx::mbar_wait(&bars[kQkFull + g], 0);
-      ptx::tcgen05_fence_after();
-      issue_s(0);
-#pragma unroll 1
-      for (int i = 0; i < n; ++i) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-#pragma unroll
-          for (int c = 0; c < NCHK; ++c) {
-            // one completion per tile: parity = tile.  Latency-critical (the group waits for this P V): spin on the
-            // non-suspending test instead of try_wait, whose wake-up costs far more than the MMAs it gates
-            while (!ptx::mbar_test_wait(&bars[kPChunk + NCHK * g + c], t)) {}
-            if (c == 0) {  // the first P V of a tile overwrites O (the previous tile's must have been read) and needs V
-              if (t == 0) {
-                ptx::mbar_wait(&bars[kVFull + g], i & 1);
-                if (i > 0) ptx::mbar_wait(&bars[kOEmpty + g], 1);
-              } else {
-                ptx::mbar_wait(&bars[kOEmpty + g], 0);
-              }
-            }
-            ptx::tcgen05_fence_after();
-            issue_o_chunk(c);
-          }
-          ptx::umma_commit(&bars[kOFull + g]);
-          if (t == 0) {
-            issue_s(1);  // executes after P V (MMAs of one thread run in order): S may overwrite P
-            ptx::umma_commit(&bars[kQkEmpty + g]);
-            if (i + 1 < n) {  // both S of the unit done: Q and K are free for the next unit of this slot
-              ptx::mbar_wait(&bars[kQkEmpty + g], i & 1);
-              load_qk(i + 1);
-            }
-          } else {
-            ptx::umma_commit(&bars[kVEmpty + g]);
-            if (i + 1 < n) {
-              ptx::mbar_wait(&bars[kQkFull + g], (i + 1) & 1);  // requested a tile ago
-              ptx::tcgen05_fence_after();
-              issue_s(0);                                       // the next unit's first S, behind this unit's last P V
-              ptx::mbar_wait(&bars[kVEmpty + g], i & 1);        // both P V done: V is free
-              load_v(i + 1);
-            }
-          }
-        }
-      }
-    };
-    if (lane == 0) {
-      if (warp == 0) drive(std::integral_constant<int, 0>{});
-      else drive(std::integral_constant<int, 1>{});
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax groups
-    const int g = (warp - 2) >> 3;
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int hf = ((warp - 2) & 7) >> 2;    // which half of the keys / of the O columns
-    const int row = q * 32 + lane;           // query row of the tile = TMEM lane
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t t_s = tmem_base + g * Cfg::SLOT_COLS, t_o = t_s + 192;
-    float* x_max = reinterpret_cast<float*>(smem + Cfg::OFF_X) + g * 512;  // [half][row]
-    float* x_sum = x_max + 256;
-    // exp2 argument scale: d_h^-0.5 * log2(e); FP16X3 scores carry the operand scale 64 * 64
-    const float c_exp = rsqrtf((float)DH) * 1.4426950408889634f * (SPLIT == 3 ? kAccScaleInv : 1.0f);
-    const float p_exp = SPLIT == 3 ? 6.0f : 0.0f;  // P leaves the exponential already in operand units (x 2^6)
-    constexpr int NCH = kNTok / 32, CHH = NCH / 2;  // 32-key chunks per row / per half
-#pragma unroll 1
-    for (int i = 0; i < n_slot[g]; ++i) {
-      const int unit = (int)blockIdx.x + (2 * i + g) * (int)gridDim.x;
-      const int b = unit / heads, h = unit % heads;
-#pragma unroll 1
-      for (int tile = 0; tile < 2; ++tile) {
-        const bool active = tile == 0 || q < 2;  // tile 1: only rows 128..191 are real
-        const bool tr = trace != nullptr && blockIdx.x == 0 && g == 0 && q == 0 && hf == 0 && lane == 0 && i < 4;
-        long long* trp = trace + (i * 2 + tile) * 8;
-        if (tr) trp[0] = clock64();
-        ptx::mbar_wait(&bars[kSFull + g], tile);  // two S per unit: the phase parity is the tile index
-        ptx::tcgen05_fence_after();
-        if (tr) trp[1] = clock64();
-        if (active) {
-          float mx = -INFINITY;
-#pragma unroll
-          for (int ch = hf * CHH; ch < (hf + 1) * CHH; ++ch) {
-            float v[32];
-            ptx::tmem_ld_32x32b_x32(t_s + lane_base + 32 * ch, v);
-            float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
-#pragma unroll
-            for (int k = 0; k < 32; k += 8) {
-              m4[0] = fmaxf(m4[0], fmaxf(v[k], v[k + 1])); m4[1] = fmaxf(m4[1], fmaxf(v[k + 2], v[k + 3]));
-              m4[2] = fmaxf(m4[2], fmaxf(v[k + 4], v[k + 5])); m4[3] = fmaxf(m4[3], fmaxf(v[k + 6], v[k + 7]));
-            }
-            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          }
-          x_max[hf * 128 + row] = mx;
-          // the two halves of a row live in warps w and w + 4 of the group: only those 64 threads have to meet
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * g) : "memory");
-          mx = fmaxf(mx, x_max[(hf ^ 1) * 128 + row]);
-          float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains (fixed order: deterministic)
-          const uint64_t nmx2 = pk2(-mx, -mx), ce2 = pk2(c_exp, c_exp), pe2 = pk2(p_exp, p_exp);
-#pragma unroll
-          for (int ch = hf * CHH; ch < (hf + 1) * CHH; ++ch) {
-            float v[32];
-            ptx::tmem_ld_32x32b_x32(t_s + lane_base + 32 * ch, v);
-            {  // exp2(((s - max) * c) + p) and the row-sum chains on packed fp32 pairs (FFMA2 / FADD2)
-              uint64_t la = pk2(l4[0], l4[1]), lb = pk2(l4[2], l4[3]);
-#pragma unroll
-              for (int k = 0; k < 32; k += 2) {
-                float a, bb;
-                upk2(fma2(add2(pk2(v[k], v[k + 1]), nmx2), ce2, pe2), a, bb);
-                v[k] = ex2f(a);
-                v[k + 1] = ex2f(bb);
-                if ((k & 2) == 0) la = add2(la, pk2(v[k], v[k + 1]));
-                else lb = add2(lb, pk2(v[k], v[k + 1]));
-              }
-              upk2(la, l4[0], l4[1]);
-              upk2(lb, l4[2], l4[3]);
-            }
-            if (ch > hf * CHH) {  // the previous chunk's P has long been stored: hand it to the slot driver (P V runs under this pass)
-              tmem_st_wait();
-              ptx::tcgen05_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&bars[kPChunk + NCH * g + ch - 1]);
-            }
-            if constexpr (SPLIT == 3) {
-              uint32_t r[32];
-#pragma unroll
-              for (int k = 0; k < 16; ++k) split_pair(v[2 * k], v[2 * k + 1], r[k], r[16 + k]);
-              tmem_st<32>(t_s + lane_base + 32 * ch, r);
-            } else {
-              uint32_t r[16];
-#pragma unroll
-              for (int k = 0; k < 16; ++k) r[k] = pack_pair<BF16>(v[2 * k], v[2 * k + 1]);
-              tmem_st<16>(t_s + lane_base + 32 * ch, r);
-            }
-          }
-          x_sum[hf * 128 + row] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-          tmem_st_wait();
-        }
-        if (tr) trp[2] = clock64();
-        ptx::tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {  // this half's last chunk; a warp without real rows in this tile (tile 1, rows 192..) signals all of its chunks here
-          if (!active) {
-#pragma unroll
-            for (int c = hf * CHH; c + 1 < (hf + 1) * CHH; ++c) ptx::mbar_arrive(&bars[kPChunk + NCH * g + c]);
-          }
-          ptx::mbar_arrive(&bars[kPChunk + NCH * g + (hf + 1) * CHH - 1]);
-        }
-        ptx::mbar_wait(&bars[kOFull + g], tile);  // also orders the row-sum halves: both warps of a row arrived on a P chunk barrier first
-        ptx::tcgen05_fence_after();
-        if (tr) trp[3] = clock64();
-        if (active) {
-          // FP16X3: O carries 64 (P) * 64 (V) and the row sum carries 64, so O / l is already in operand units
-          const float inv = 1.0f / (x_sum[row] + x_sum[128 + row]);
-          const size_t orow = (size_t)b * kNTok + tile * 128 + row;
-          uint16_t* d = out_op + orow * (NOPS * D) + h * DH + hf * (DH / 2);  // this thread's half of the head's columns
-          constexpr int HC = DH / 2;  // 16 columns per thread and block
-          uint32_t o_a[16], o_b[16];
-          tmem_ld_x16_issue(t_o + lane_base + hf * HC, o_a);
-          if constexpr (SPLIT == 3) tmem_ld_x16_issue(t_o + lane_base + DH + hf * HC, o_b);  // [P V_hi + P_lo V_hi | P_hi V_lo]
-          tmem_ld_wait();
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float o0 = __uint_as_float(o_a[2 * k]), o1 = __uint_as_float(o_a[2 * k + 1]);
-            if constexpr (SPLIT == 3) {
-              o0 += __uint_as_float(o_b[2 * k]);
-              o1 += __uint_as_float(o_b[2 * k + 1]);
-            }
-            o0 *= inv;
-            o1 *= inv;
-            if constexpr (SPLIT == 3) split_pair(o0, o1, hi[k], lo[k]);
-            else hi[k] = pack_pair<BF16>(o0, o1);
-          }
-          st_global_v8(d, hi);  // 16 columns = one whole 32-byte sector per plane
-          if constexpr (SPLIT == 3) st_global_v8(d + D, lo);
-        }
-        ptx::tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars[kOEmpty + g]);  // O has been read: the next P V may overwrite it
-        if (tr) trp[4] = clock64();
-      }
-    }
-  }
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-template <int DH, int SPLIT, bool BF16>
-int launch_ws(const void* qkv_op, int batch, int heads, void* out_op, cudaStream_t st) {
-  using Cfg = WsCfg<DH, SPLIT>;
-  auto kern = attention_ws_kernel<DH, SPLIT, BF16>;
-  static PerDeviceOnce attr_set;
-  if (attr_set.first()) PP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int64_t rows = (int64_t)batch * kNTok, row_elems = (int64_t)Cfg::NOPS * 3 * heads * DH;
-  CUtensorMap tq, tkv;
-  int rc = make_operand_map(&tq, qkv_op, rows, row_elems, 128, DH, BF16);
-  if (rc) return rc;
-  rc = make_operand_map(&tkv, qkv_op, rows, row_elems, kNTok, DH, BF16);
-  if (rc) return rc;
-  const int units = batch * heads;
-  const int sms = num_sms_att();
-  long long* trace = nullptr;  // PP_ATT_TRACE=<device pointer>: clock stamps of CTA 0 / group 0 (profiling only)
-  if (const char* e = getenv("PP_ATT_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  PP_CHECK_CUDA(launch_pdl(kern, dim3(units < sms ? units : sms), dim3(kWsThreads), Cfg::SMEM_BYTES, st, tq, tkv, heads, units,
-                           reinterpret_cast<uint16_t*>(out_op), trace));
-  count_launch();
-  PP_CHECK_CUDA(cudaGetLastError());
-  return PP_OK;
-}
-
 template <int DH, int SPLIT, bool BF16>
 int launch_tc(const void* qkv_op, int batch, int heads, void* out_op, cudaStream_t st) {
   using Cfg = AttCfg<DH, SPLIT>;
@@ -820,22 +433,8 @@ int launch_tc(const void* qkv_op, int batch, int heads, void* out_op, cudaStream
   return PP_OK;
 }
 
-static bool use_ws_kernel() {  // PP_ATTENTION=tc1 keeps the two-CTAs-per-SM kernel at head width 32 (A/B timing)
-  static const bool on = !(getenv("PP_ATTENTION") && strcmp(getenv("PP_ATTENTION"), "tc1") == 0);
-  return on;
-}
-
 template <int DH>
 int launch_tc_prec(int prec, const void* qkv_op, int batch, int heads, void* out_op, cudaStream_t st) {
-  if constexpr (DH == 32) {
-    if (use_ws_kernel()) {
-      switch (prec) {
-        case PP_PREC_FP16X3: return launch_ws<32, 3, false>(qkv_op, batch, heads, out_op, st);
-        case PP_PREC_BF16: return launch_ws<32, 1, true>(qkv_op, batch, heads, out_op, st);
-        case PP_PREC_FP16: return launch_ws<32, 1, false>(qkv_op, batch, heads, out_op, st);
-      }
-    }
-  }
   switch (prec) {
     case PP_PREC_FP16X3: return launch_tc<DH, 3, false>(qkv_op, batch, heads, out_op, st);
     case PP_PREC_BF16: return launch_tc<DH, 1, true>(qkv_op, batch, heads, out_op, st);

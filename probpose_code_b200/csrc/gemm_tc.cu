@@ -192,7 +192,9 @@ template <int PREC>
 __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int col, int k, float4 v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
     uint2 hi, lo;
+#ifndef PP_NO_GEMM_GUARD
     note_overflow4(v.x, v.y, v.z, v.w);  // the conversion below clamps: never silently
+#endif
     hi.x = pack_half2_sat(v.x, v.y); hi.y = pack_half2_sat(v.z, v.w);
     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
     float r0, r1, r2, r3;  // residues v - hi: exact, one packed subtraction per pair
