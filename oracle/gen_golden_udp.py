@@ -55,6 +55,7 @@ def main():
         "gauss": udp_oracle.gaussian_heatmaps(8, seed=0),
         "gauss_noisy": udp_oracle.gaussian_heatmaps(4, seed=1, noise=0.05),
         "special": udp_oracle.special_heatmaps(),
+        "noresp": udp_oracle.no_response_heatmaps(),
     }
     a, b = udp_oracle.gaussian_heatmaps(4, seed=2), udp_oracle.gaussian_heatmaps(4, seed=2, noise=0.02)
     inv = np.argsort(udp_oracle.COCO_FLIP_INDICES)

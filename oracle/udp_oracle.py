@@ -57,6 +57,33 @@ def gaussian_blur(heatmaps: np.ndarray, kernel: int = 11) -> np.ndarray:
     return heatmaps
 
 
+def gaussian_blur_exact(img: np.ndarray, kernel: int = 11) -> np.ndarray:
+    """cv2.GaussianBlur(zero-padded img, (kernel, kernel), 0) cropped back, WITHOUT OpenCV, bit for bit: the float
+    arithmetic of OpenCV's CV_32F filter engine (AVX2 / FMA3 build) is, per output pixel,
+      row filter     s = x[0] k[0];  s = fma(x[j], k[j], s), j = 1 .. kernel - 1          (general form)
+      column filter  s = r[c] k[c];  s = fma(r[c + d] + r[c - d], k[c + d], s), d = 1 .. radius   (symmetric form)
+    (found by trying the four combinations against cv2, tests/test_oracle_udp.py keeps it pinned).  This is the
+    arithmetic csrc/decode_udp.cu implements; fma is emulated in float64 (the product of two float32 is exact there)."""
+    k = gaussian_kernel_1d(kernel)
+    b = (kernel - 1) // 2
+    h, w = img.shape
+
+    def fma(a, t, c):
+        return (a.astype(np.float64) * np.float64(t) + c.astype(np.float64)).astype(np.float32)
+
+    xp = np.zeros((h, w + 2 * b), np.float32)
+    xp[:, b:-b] = img
+    rows = (xp[:, 0:w] * k[0]).astype(np.float32)
+    for j in range(1, kernel):
+        rows = fma(xp[:, j:j + w], k[j], rows)
+    rp = np.zeros((h + 2 * b, w), np.float32)
+    rp[b:-b] = rows
+    out = (rp[b:b + h] * k[b]).astype(np.float32)
+    for d in range(1, b + 1):
+        out = fma((rp[b + d:b + d + h] + rp[b - d:b - d + h]).astype(np.float32), k[b + d], out)
+    return out
+
+
 def refine_dark_udp(keypoints: np.ndarray, heatmaps: np.ndarray, blur_kernel_size: int = 11) -> np.ndarray:
     """refinement.py:102-160 (keypoints (N, K, 2) float32 in place, heatmaps (K, H, W) modified in place)."""
     n_inst, k = keypoints.shape[:2]
@@ -145,6 +172,23 @@ def gaussian_heatmaps(batch: int, seed: int = 0, sigma: float = 2.0, noise: floa
     yy, xx = np.mgrid[0:H, 0:W]
     r2 = (xx[None, None] - cx) ** 2 + (yy[None, None] - cy) ** 2
     return (a * np.exp(-r2 / (2 * sigma**2)) + rng.normal(0, noise, (batch, K, H, W))).astype(np.float32)
+
+
+def no_response_heatmaps():
+    """(2, K, H, W): maps whose maximum is <= 0 (all-zero, all-negative, zero with negative dips) next to ordinary ones -
+    get_heatmap_maximum marks them (-1, -1) and refine_keypoints_dark_udp then reads samples that wrap into the previous
+    keypoint's padded plane (refinement.py:130-138 on index 0; keypoint K - 1 for keypoint 0)."""
+    hm = gaussian_heatmaps(2, seed=5)
+    rng = np.random.default_rng(6)
+    hm[0, 0] = 0.0
+    hm[0, 3] = -0.25
+    hm[0, 4] = -np.abs(rng.normal(0, 0.1, (H, W))).astype(np.float32)
+    hm[0, 9] = 0.0
+    hm[0, 9, 5:9, 7:11] = -1.0
+    hm[1, 16] = 0.0
+    hm[1, 0] = -1e-3
+    hm[1, 1] = 0.0  # two no-response maps in a row: the neighbour is one as well
+    return hm
 
 
 def special_heatmaps():

@@ -2,7 +2,8 @@
 //
 //   merged = 0.5 * (H + mirror(Hf[flip_idx[k]]))                       (flip-TTA, heatmap_head.py:245-256, tta.py:35-39)
 //   (x, y) = first arg max of merged, score = max ; (-1, -1) if max <= 0  (post_processing.py:178-217)
-//   B = zero-padded separable Gaussian blur (OpenCV float taps), rescaled to the old maximum (post_processing.py:220-249)
+//   B = zero-padded separable Gaussian blur, bit for bit cv2.GaussianBlur's float arithmetic, rescaled to the old
+//       maximum (post_processing.py:220-249)
 //   L = log(clip(B, 1e-3, 50)), edge-padded ; gradient / Hessian of L at the peak from 7 samples ;
 //   (x, y) -= pinv(Hessian + eps I) grad                                 (refinement.py:102-160)
 //   record = [x, y, score]   (heatmap pixels; the caller applies udp_heatmap.py:194-195 in double)
@@ -35,7 +36,7 @@ struct UdpParams {
 };
 
 template <int H, int W>
-__global__ void __launch_bounds__(kUdpThreads, 4) udp_decode_kernel(const __grid_constant__ UdpParams p) {
+__global__ void __launch_bounds__(kUdpThreads, 3) udp_decode_kernel(const __grid_constant__ UdpParams p) {
   constexpr int NPX = H * W, NV4 = NPX / 4, V = NV4 / kUdpThreads;
   static_assert(NV4 % kUdpThreads == 0 && W % 4 == 0, "map must split into whole float4 per thread");
   __shared__ __align__(16) float sP[NPX];  // merged heatmap
@@ -51,139 +52,180 @@ __global__ void __launch_bounds__(kUdpThreads, 4) udp_decode_kernel(const __grid
   const bool tta = p.maps_flip != nullptr;
   pdl_wait();
 
-  {
-    const float4* s1 = reinterpret_cast<const float4*>(p.maps + (size_t)item * NPX);
+  // One map through merge -> first maximum -> blur (sP merged map, sC blurred map); every thread returns the map's
+  // maximum, its first flat index and the maximum of the blurred map.
+  auto process = [&](int it, bool write_merged, float& best_out, int& best_i_out, float& bmax_out) {
+    const int bb = it / K, kk = it % K;
+    {
+      const float4* s1 = reinterpret_cast<const float4*>(p.maps + (size_t)it * NPX);
 #pragma unroll
-    for (int j = 0; j < V; ++j) reinterpret_cast<float4*>(sP)[tid + j * kUdpThreads] = ld_stream_f4(s1 + tid + j * kUdpThreads);
-    if (tta) {
-      const float4* s2 = reinterpret_cast<const float4*>(p.maps_flip + (size_t)(b * K + p.flip_idx[k]) * NPX);
-      float4 z[V];
+      for (int j = 0; j < V; ++j) reinterpret_cast<float4*>(sP)[tid + j * kUdpThreads] = ld_stream_f4(s1 + tid + j * kUdpThreads);
+      if (tta) {
+        const float4* s2 = reinterpret_cast<const float4*>(p.maps_flip + (size_t)(bb * K + p.flip_idx[kk]) * NPX);
+        float4 z[V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) z[j] = ld_stream_f4(s2 + tid + j * kUdpThreads);
-      __syncthreads();
+        for (int j = 0; j < V; ++j) z[j] = ld_stream_f4(s2 + tid + j * kUdpThreads);
+        __syncthreads();
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const int v4 = tid + j * kUdpThreads, y = v4 / (W / 4), xq = v4 % (W / 4);
-        const int dst = y * (W / 4) + (W / 4 - 1 - xq);  // mirrored float4 slot, components reversed
-        float4 a = reinterpret_cast<float4*>(sP)[dst];
-        a.x = (a.x + z[j].w) * 0.5f; a.y = (a.y + z[j].z) * 0.5f; a.z = (a.z + z[j].y) * 0.5f; a.w = (a.w + z[j].x) * 0.5f;
-        reinterpret_cast<float4*>(sP)[dst] = a;
+        for (int j = 0; j < V; ++j) {
+          const int v4 = tid + j * kUdpThreads, y = v4 / (W / 4), xq = v4 % (W / 4);
+          const int dst = y * (W / 4) + (W / 4 - 1 - xq);  // mirrored float4 slot, components reversed
+          float4 a = reinterpret_cast<float4*>(sP)[dst];
+          a.x = (a.x + z[j].w) * 0.5f; a.y = (a.y + z[j].z) * 0.5f; a.z = (a.z + z[j].y) * 0.5f; a.w = (a.w + z[j].x) * 0.5f;
+          reinterpret_cast<float4*>(sP)[dst] = a;
+        }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- first maximum of the merged map (smallest flat index among equal maxima) ----
-  float best = -INFINITY;
-  int best_i = 0x7fffffff;
-  float4* gout = p.merged_out ? reinterpret_cast<float4*>(p.merged_out + (size_t)item * NPX) : nullptr;
+    // ---- first maximum of the merged map (smallest flat index among equal maxima) ----
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    float4* gout = (write_merged && p.merged_out) ? reinterpret_cast<float4*>(p.merged_out + (size_t)it * NPX) : nullptr;
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const int v4 = tid + j * kUdpThreads;
-    const float4 a = reinterpret_cast<const float4*>(sP)[v4];
-    if (gout) gout[v4] = a;
-    const float e[4] = {a.x, a.y, a.z, a.w};
+    for (int j = 0; j < V; ++j) {
+      const int v4 = tid + j * kUdpThreads;
+      const float4 a = reinterpret_cast<const float4*>(sP)[v4];
+      if (gout) gout[v4] = a;
+      const float e[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (e[c] > best) { best = e[c]; best_i = 4 * v4 + c; }  // ascending index per thread
-  }
-  // NaN-free inputs assumed (np.argmax would return the first NaN)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-  }
-  if (lane == 0) { red_v[warp] = best; red_i[warp] = best_i; }
-
-  // ---- row pass of the blur (zero outside the map), register-blocked: a thread owns RB consecutive outputs of one
-  // row and slides over RB + ntaps - 1 inputs held in registers - one shared-memory read per input, not per tap ----
-  const int rad = p.ntaps >> 1;
-  constexpr int RB = 12;                       // W / RB segments per row
-  static_assert(W % RB == 0 && (H * (W / RB)) % kUdpThreads == 0, "row segments must tile the block");
-  constexpr int kWin = RB + kUdpMaxTaps - 1;
-  for (int sgm = tid; sgm < H * (W / RB); sgm += kUdpThreads) {
-    const int y = sgm / (W / RB), x0 = (sgm % (W / RB)) * RB;
-    const float* row = sP + y * W;
-    float win[kWin];
-#pragma unroll
-    for (int i = 0; i < kWin; ++i) {
-      const int xx = x0 - rad + i;
-      win[i] = (i < RB + 2 * rad && xx >= 0 && xx < W) ? row[xx] : 0.f;
+      for (int c = 0; c < 4; ++c)
+        if (e[c] > best) { best = e[c]; best_i = 4 * v4 + c; }  // ascending index per thread
     }
-    float acc[RB];
+    // NaN-free inputs assumed (np.argmax would return the first NaN)
 #pragma unroll
-    for (int o = 0; o < RB; ++o) acc[o] = 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0) { red_v[warp] = best; red_i[warp] = best_i; }
+
+    // ---- the blur, bit for bit as cv2.GaussianBlur computes it for CV_32F (its AVX2 / FMA3 filter engine; verified
+    // against cv2 on the host, see oracle/udp_oracle.py:gaussian_blur_exact): the ROW filter is the general form -
+    // s = x[0] k[0], then s = fma(x[j], k[j], s) for j ascending - and the COLUMN filter the symmetric form -
+    // s = r[c] k[c], then s = fma(r[c + d] + r[c - d], k[c + d], s) for d = 1 .. radius.  Zero outside the map (the
+    // reference pads the map with a radius-wide zero frame before it calls OpenCV, so the border mode never matters).
+    // Register-blocked: a thread owns RB consecutive outputs of one row and slides over RB + ntaps - 1 inputs held in
+    // registers - one shared-memory read per input, not per tap ----
+    const int rad = p.ntaps >> 1;
+    constexpr int RB = 12;                       // W / RB segments per row
+    static_assert(W % RB == 0 && (H * (W / RB)) % kUdpThreads == 0, "row segments must tile the block");
+    constexpr int kWin = RB + kUdpMaxTaps - 1;
+    for (int sgm = tid; sgm < H * (W / RB); sgm += kUdpThreads) {
+      const int y = sgm / (W / RB), x0 = (sgm % (W / RB)) * RB;
+      const float* row = sP + y * W;
+      float win[kWin];
 #pragma unroll
-    for (int j = 0; j < kUdpMaxTaps; ++j) {
-      if (j < p.ntaps) {  // block-uniform
-        const float t = p.taps[j];
+      for (int i = 0; i < kWin; ++i) {
+        const int xx = x0 - rad + i;
+        win[i] = (i < RB + 2 * rad && xx >= 0 && xx < W) ? row[xx] : 0.f;
+      }
+      float acc[RB];
 #pragma unroll
-        for (int o = 0; o < RB; ++o) acc[o] = fmaf(win[o + j], t, acc[o]);
+      for (int o = 0; o < RB; ++o) acc[o] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kUdpMaxTaps; ++j) {
+        if (j < p.ntaps) {  // block-uniform
+          const float t = p.taps[j];
+#pragma unroll
+          for (int o = 0; o < RB; ++o) acc[o] = fmaf(win[o + j], t, acc[o]);  // j = 0: fma(x, k, 0) = the rounded product
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < RB; ++o) sR[y * W + x0 + o] = acc[o];
+    }
+    __syncthreads();
+    // ---- column pass, maximum of the blurred map: a thread owns CB consecutive rows of one column ----
+    float bmax = -INFINITY;
+    constexpr int CB = 16;
+    static_assert(H % CB == 0, "column segments");
+    constexpr int kWinC = CB + kUdpMaxTaps - 1;
+    constexpr int kMaxRad = kUdpMaxTaps / 2;
+    for (int sgm = tid; sgm < W * (H / CB); sgm += kUdpThreads) {
+      const int x = sgm % W, y0 = (sgm / W) * CB;  // consecutive threads -> consecutive columns: conflict-free
+      // the window is centred at a compile-time position (tap radius kMaxRad) so that win[] stays in registers
+      float win[kWinC];
+#pragma unroll
+      for (int i = 0; i < kWinC; ++i) {
+        const int yy = y0 - kMaxRad + i;
+        win[i] = (i >= kMaxRad - rad && i < CB + kMaxRad + rad && yy >= 0 && yy < H) ? sR[yy * W + x] : 0.f;
+      }
+      float acc[CB];
+      {
+        const float tc = p.taps[rad];
+#pragma unroll
+        for (int o = 0; o < CB; ++o) acc[o] = __fmul_rn(win[o + kMaxRad], tc);
+      }
+#pragma unroll
+      for (int d = 1; d <= kMaxRad; ++d) {
+        if (d <= rad) {  // block-uniform
+          const float t = p.taps[rad + d];
+#pragma unroll
+          for (int o = 0; o < CB; ++o) acc[o] = fmaf(__fadd_rn(win[o + kMaxRad + d], win[o + kMaxRad - d]), t, acc[o]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < CB; ++o) {
+        sC[(y0 + o) * W + x] = acc[o];
+        bmax = fmaxf(bmax, acc[o]);
       }
     }
-#pragma unroll
-    for (int o = 0; o < RB; ++o) sR[y * W + x0 + o] = acc[o];
-  }
-  __syncthreads();
-  // ---- column pass, maximum of the blurred map: a thread owns CB consecutive rows of one column ----
-  float bmax = -INFINITY;
-  constexpr int CB = 16;
-  static_assert(H % CB == 0, "column segments");
-  constexpr int kWinC = CB + kUdpMaxTaps - 1;
-  for (int sgm = tid; sgm < W * (H / CB); sgm += kUdpThreads) {
-    const int x = sgm % W, y0 = (sgm / W) * CB;  // consecutive threads -> consecutive columns: conflict-free
-    float win[kWinC];
-#pragma unroll
-    for (int i = 0; i < kWinC; ++i) {
-      const int yy = y0 - rad + i;
-      win[i] = (i < CB + 2 * rad && yy >= 0 && yy < H) ? sR[yy * W + x] : 0.f;
-    }
-    float acc[CB];
-#pragma unroll
-    for (int o = 0; o < CB; ++o) acc[o] = 0.f;
-#pragma unroll
-    for (int j = 0; j < kUdpMaxTaps; ++j) {
-      if (j < p.ntaps) {
-        const float t = p.taps[j];
-#pragma unroll
-        for (int o = 0; o < CB; ++o) acc[o] = fmaf(win[o + j], t, acc[o]);
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < CB; ++o) {
-      sC[(y0 + o) * W + x] = acc[o];
-      bmax = fmaxf(bmax, acc[o]);
-    }
-  }
-  bmax = warp_max(bmax);
-  if (lane == 0) red_b[warp] = bmax;
-  __syncthreads();
-
-  if (tid == 0) {
-    for (int w = 0; w < kUdpWarps; ++w) {
+    bmax = warp_max(bmax);
+    if (lane == 0) red_b[warp] = bmax;
+    __syncthreads();
+    for (int w = 0; w < kUdpWarps; ++w) {  // every thread: the same final values
       if (red_v[w] > best || (red_v[w] == best && red_i[w] < best_i)) { best = red_v[w]; best_i = red_i[w]; }
       bmax = fmaxf(bmax, red_b[w]);
     }
+    best_out = best; best_i_out = best_i; bmax_out = bmax;
+  };
+  // log of the clipped, rescaled blurred map in sC, edge-padded (refinement.py:123-127).  The rescale
+  // heatmaps[k] *= origin_max / (np.max(heatmaps[k]) + 1e-12) (post_processing.py:247) is float32 arithmetic end to end
+  // under NumPy 2 promotion rules (the python float 1e-12 is "weak": float32 + 1e-12 stays float32; this image ships
+  // NumPy 2.3, and the oracle is pinned to the reference run under it)
+  auto L_at = [&](int y, int x, float scale) -> float {
+    y = min(max(y, 0), H - 1);
+    x = min(max(x, 0), W - 1);
+    const float v = __fmul_rn(sC[y * W + x], scale);
+    // the correctly rounded float logarithm (double log, rounded once): numpy's float32 log is correctly rounded for
+    // all but a few inputs, CUDA's logf (1 ulp) for fewer - and a flat map's Hessian amplifies every ulp
+    return (float)log((double)fminf(fmaxf(v, 1e-3f), 50.0f));
+  };
+
+  float best, bmax;
+  int best_i;
+  process(item, true, best, best_i, bmax);
+  const float scale = __fdiv_rn(best, __fadd_rn(bmax, 1e-12f));
+  float i_, ix1, iy1, ix1y1, ix1_y1_, ix1_, iy1_;
+  float px_f, py_f;
+  if (best > 0.f) {
+    const int py = best_i / W, px = best_i % W;
+    px_f = (float)px; py_f = (float)py;
+    i_ = L_at(py, px, scale); ix1 = L_at(py, px + 1, scale); iy1 = L_at(py + 1, px, scale); ix1y1 = L_at(py + 1, px + 1, scale);
+    ix1_y1_ = L_at(py - 1, px - 1, scale); ix1_ = L_at(py, px - 1, scale); iy1_ = L_at(py - 1, px, scale);
+  } else {
+    // No response (maximum <= 0): get_heatmap_maximum marks the keypoint (-1, -1) (post_processing.py:213-215), and the
+    // refinement then indexes the FLATTENED edge-padded stack of the K maps at (-1 + 1) + (-1 + 1) (W + 2) = the first
+    // element of map k's padded plane (refinement.py:130-138): the four "forward" samples are this map's corner
+    // L(0, 0), the three "backward" samples fall off the front of the plane into the END of the previous keypoint's
+    // padded plane (keypoint K - 1 for k = 0: negative indices wrap in numpy) - its bottom-right corner, bottom-left
+    // corner and bottom-right corner again.  Reproduced as it is: the previous map goes through the same pipeline.
+    px_f = -1.f; py_f = -1.f;
+    i_ = ix1 = iy1 = ix1y1 = L_at(0, 0, scale);
+    __syncthreads();  // every thread is done with this map's planes
+    float nbest, nbmax;
+    int nbest_i;
+    process(b * K + (k + K - 1) % K, false, nbest, nbest_i, nbmax);
+    const float nscale = __fdiv_rn(nbest, __fadd_rn(nbmax, 1e-12f));
+    ix1_ = L_at(H - 1, W - 1, nscale);      // flat index - 1:       padded (H + 1, W + 1) of the previous map
+    iy1_ = L_at(H - 1, 0, nscale);          // flat index - (W + 2): padded (H + 1, 0)
+    ix1_y1_ = L_at(H - 1, W - 1, nscale);   // flat index - (W + 3): padded (H, W + 1)
+  }
+  if (tid == 0) {
     float* rec = p.records + (size_t)item * 3;
     rec[2] = best;
-    if (!(best > 0.f)) {
-      // No response: the reference marks the keypoint (-1, -1) and then "refines" it with samples that wrap around
-      // into the neighbouring keypoint's map (refinement.py:130-138 on index 0) - not reproduced.
-      rec[0] = -1.f;
-      rec[1] = -1.f;
-    } else {
-      const int py = best_i / W, px = best_i % W;
-      // heatmaps[k] *= origin_max / (max + 1e-12): a float64 scalar times the float32 map, rounded to float32
-      const double scale = (double)best / ((double)bmax + 1e-12);
-      auto L = [&](int y, int x) -> float {  // log of the clipped, rescaled blurred map, edge-padded
-        y = min(max(y, 0), H - 1);
-        x = min(max(x, 0), W - 1);
-        const float v = (float)((double)sC[y * W + x] * scale);
-        return logf(fminf(fmaxf(v, 1e-3f), 50.0f));
-      };
-      const float i_ = L(py, px), ix1 = L(py, px + 1), iy1 = L(py + 1, px), ix1y1 = L(py + 1, px + 1);
-      const float ix1_y1_ = L(py - 1, px - 1), ix1_ = L(py, px - 1), iy1_ = L(py - 1, px);
+    {
       const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_)), dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
       const float dxx = __fadd_rn(__fsub_rn(ix1, __fmul_rn(2.f, i_)), ix1_);
       const float dyy = __fadd_rn(__fsub_rn(iy1, __fmul_rn(2.f, i_)), iy1_);
@@ -214,8 +256,8 @@ __global__ void __launch_bounds__(kUdpThreads, 4) udp_decode_kernel(const __grid
         ox = vx * proj;
         oy = vy * proj;
       }
-      rec[0] = (float)((double)(float)px - ox);
-      rec[1] = (float)((double)(float)py - oy);
+      rec[0] = (float)((double)px_f - ox);
+      rec[1] = (float)((double)py_f - oy);
     }
   }
 }

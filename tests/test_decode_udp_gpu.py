@@ -1,6 +1,8 @@
 """pp_decode_udp (fused flip-TTA merge + DARK-UDP decode) against the oracle, which is pinned bit-for-bit to the genuine
-reference code (tests/test_oracle_udp.py).  Tolerance: 1e-3 input pixels on keypoints (the blur runs in fp32 with a
-different summation order than OpenCV's SIMD filter), scores bit-equal."""
+reference code (tests/test_oracle_udp.py).  The blur reproduces cv2.GaussianBlur's float arithmetic bit for bit, so the
+only rounding left between kernel and reference is logf (CUDA's vs numpy's float32 log, <= 1 ulp each).  Tolerance:
+1e-3 input pixels on EVERY map - corners, ties, clipped maps, and maps without a response (maximum <= 0), where the
+reference's index arithmetic wraps into the previous keypoint's map; scores bit-equal."""
 import numpy as np
 import pytest
 import torch
@@ -16,19 +18,15 @@ def _to_input(rec):  # udp_heatmap.py:194-195 in double
 
 
 @pytest.mark.parametrize("name,hms", [("gauss", u.gaussian_heatmaps(6, seed=0)), ("noisy", u.gaussian_heatmaps(3, seed=1, noise=0.05)),
-                                      ("special", u.special_heatmaps())])
+                                      ("special", u.special_heatmaps()), ("noresp", u.no_response_heatmaps())])
 def test_udp_decode_matches_oracle(name, hms):
     from probpose_code_b200 import ops
     rec = ops.decode_udp(torch.from_numpy(hms).cuda()).cpu().numpy()
     kp, sc = u.decode_instances(hms)
     kp, sc = np.concatenate(kp), np.concatenate(sc)
     np.testing.assert_array_equal(rec[..., 2], sc)
-    # maps around the clip at 1e-3 / with a flat 2-pixel top have a (near-)singular Hessian: excluded from the px bound
-    ok = np.ones(kp.shape[:2], bool)
-    if name == "special":
-        ok[0, [10, 11, 15]] = False
     d = np.abs(_to_input(rec) - kp).max(-1)
-    assert d[ok].max() <= 1e-3, f"max keypoint deviation {d[ok].max()} px"
+    assert d.max() <= 1e-3, f"max keypoint deviation {d.max()} px at {np.unravel_index(d.argmax(), d.shape)}"
 
 
 def test_udp_decode_flip_merge_and_heatmap_output():
@@ -50,8 +48,10 @@ def test_udp_decode_no_response_and_errors():
     hm[0, 1] = -0.5
     hm[0, 2, 10, 7] = 0.25
     rec = ops.decode_udp(hm).cpu().numpy()
-    assert rec[0, 0].tolist() == [-1.0, -1.0, 0.0] and rec[0, 1].tolist() == [-1.0, -1.0, -0.5]
-    assert rec[0, 2, 2] == 0.25 and abs(rec[0, 2, 0] - 7) < 0.5 and abs(rec[0, 2, 1] - 10) < 0.5
+    kp, sc = u.decode_instances(hm.cpu().numpy())
+    assert rec[0, 0, 2] == 0.0 and rec[0, 1, 2] == -0.5 and rec[0, 2, 2] == 0.25
+    assert np.abs(_to_input(rec) - np.concatenate(kp)).max() <= 1e-3  # (-1, -1) minus the wrapped refinement step, as the reference
+    assert abs(rec[0, 2, 0] - 7) < 0.5 and abs(rec[0, 2, 1] - 10) < 0.5
     with pytest.raises(ValueError):
         ops.decode_udp(hm, hm, None)
     with pytest.raises(Exception):

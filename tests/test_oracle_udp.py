@@ -23,11 +23,12 @@ def _families():
         "gauss": u.gaussian_heatmaps(8, seed=0),
         "gauss_noisy": u.gaussian_heatmaps(4, seed=1, noise=0.05),
         "special": u.special_heatmaps(),
+        "noresp": u.no_response_heatmaps(),
         "merged": u.merge_flip(a, np.ascontiguousarray(b[:, inv][..., ::-1])),
     }
 
 
-@pytest.mark.parametrize("name", ["gauss", "gauss_noisy", "special", "merged"])
+@pytest.mark.parametrize("name", ["gauss", "gauss_noisy", "special", "noresp", "merged"])
 def test_udp_oracle_matches_reference_bit_for_bit(udp_golden, name):
     hms = _families()[name]
     assert cases.checksum(hms) == str(udp_golden[f"{name}/input_sha"]), "seeded inputs drifted from the golden run"
@@ -57,3 +58,20 @@ def test_maximum_rule():
     hm[2] = -1.0
     locs, vals = u.heatmap_maximum(hm)
     assert locs.tolist() == [[-1, -1], [3, 2], [-1, -1]] and vals.tolist() == [0.0, np.float32(0.7), -1.0]
+
+
+@pytest.mark.parametrize("ksize", [11, 17])
+def test_exact_blur_emulation_equals_cv2(ksize):
+    """oracle.udp_oracle.gaussian_blur_exact (= the arithmetic of csrc/decode_udp.cu) against cv2.GaussianBlur on the
+    reference's zero-padded image, bit for bit, on every family incl. negative maps and large magnitudes."""
+    import cv2
+    b = (ksize - 1) // 2
+    rng = np.random.default_rng(3)
+    maps = [u.gaussian_heatmaps(1, seed=7)[0, 2], u.special_heatmaps()[0, 12], u.special_heatmaps()[0, 14],
+            u.no_response_heatmaps()[0, 4], rng.normal(0, 1, (64, 48)).astype(np.float32),
+            (rng.random((64, 48)) * 1e-4).astype(np.float32)]
+    for m in maps:
+        pad = np.zeros((64 + 2 * b, 48 + 2 * b), np.float32)
+        pad[b:-b, b:-b] = m
+        want = cv2.GaussianBlur(pad, (ksize, ksize), 0)[b:-b, b:-b]
+        np.testing.assert_array_equal(u.gaussian_blur_exact(m, ksize), want)

@@ -55,14 +55,16 @@ def test_fused_predict_matches_oracle(setup, flip):
     # decode parity on identical heatmap bits (bbox = whole image, so image space == input space)
     kp_o, sc_o = udp_oracle.decode_instances(hm)
     np.testing.assert_array_equal(scores, np.concatenate(sc_o))
-    # random-init heads give flat maps whose DARK Hessian is near singular: there the refinement amplifies the
-    # float rounding of the blur (OpenCV's SIMD summation order vs ours) without bound.  The pixel tolerance is
-    # asserted where the Hessian is conditioned like a trained head's (|eig| ~ 1/8), a loose bound elsewhere.
+    # identical heatmap bits in, blur and rescale bit-identical to cv2 / NumPy: the one rounding left between kernel and
+    # reference is the float32 log (the kernel's is correctly rounded, numpy's SIMD log is not for ~2 % of its inputs),
+    # and a random-init head's flat maps have near-singular DARK Hessians that amplify that last bit.  Most keypoints
+    # are identical to ~1e-14 px; 1e-3 px wherever the Hessian is conditioned at all (|eig| >= 5e-3; a trained sigma = 2 peak
+    # has ~1/8 - tests/test_decode_udp_gpu.py asserts 1e-3 px on EVERY trained-like, special and no-response map).
     eig = np.stack([udp_oracle.hessian_min_eig(h) for h in hm])
-    well = (scores > 0) & (eig >= 0.02)
+    well = (scores > 0) & (eig >= 5e-3)
     d = np.abs(kpts - np.concatenate(kp_o)).max(-1)
-    assert well.sum() >= 3 and d[well].max() <= 1e-3, f"{d[well].max()} px on well-conditioned maps"
-    assert np.median(d[scores > 0]) <= 1e-3
+    assert well.sum() >= 3 and d[well].max() <= 1e-3, f"{d[well].max()} px on conditioned maps"
+    assert np.mean(d < 1e-6) >= 0.4 and np.median(d) <= 1e-4, "about half of these flat maps decode identically to the last bit"
     # and end to end against the oracle pipeline
     rec = ref.predict(ref.preprocess(crops), flip_test=flip)
     assert np.abs(scores - rec[..., 2]).max() <= 2e-5 * np.abs(rec[..., 2]).max()
