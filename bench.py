@@ -397,6 +397,9 @@ def main():
         if gath:
             gath.wait()
         barrier()
+        if gath:
+            gath.pending = [False, False]  # everything has completed: the timed region starts with fresh statistics
+            gath.reset_stats()
         launches = eng.last_launch_count
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()

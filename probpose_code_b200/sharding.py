@@ -86,9 +86,9 @@ class RecordGatherer:
         valid after :meth:`wait` (or after the side stream reaches this point)."""
         from ._lib import check, lib
         j = i & 1
-        if self.pending[j]:
-            self._ms += self.t0[j].elapsed_time(self.t1[j]) if self.t1[j].query() else 0.0
-            self._n += 1 if self.t1[j].query() else 0
+        if self.pending[j] and self.t1[j].query():
+            self._ms += self.t0[j].elapsed_time(self.t1[j])
+            self._n += 1
         self.decoded[j].record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.decoded[j])
@@ -105,6 +105,10 @@ class RecordGatherer:
         for j in range(2):
             if self.pending[j]:
                 cur.wait_event(self.t1[j])
+
+    def reset_stats(self) -> None:
+        """Forget the gather timings so far (the first collective of a communicator sets up its channels)."""
+        self._ms, self._n = 0.0, 0
 
     def gather_ms(self) -> Optional[float]:
         """Mean device time of a gather (side-stream events), over the gathers whose buffers have been reused."""
