@@ -190,3 +190,18 @@ def test_scattered_supports(seed):
     rec2 = _ops().decode(torch.from_numpy(z).cuda(), input_is_logits=True).cpu().numpy()
     assert np.abs(rec2[..., :2] - locs2).max() <= 2.4e-4
     np.testing.assert_allclose(rec2[..., 2], vals2, atol=2e-6)
+
+
+def test_fused_sparsemax_against_an_independent_gpu_implementation():
+    """The PyPI ``sparsemax`` package the reference imports (probmap_head.py:11) is not in the tree and cannot be
+    installed offline, so the oracle's sparsemax is a restatement of Martins & Astudillo Alg. 1.  Independent witness
+    on the GPU: liger_kernel's sort + cumsum sparsemax (a third-party Triton kernel, test infrastructure only) on the same
+    logits must give the heatmaps the fused decode kernel produces."""
+    liger = pytest.importorskip("liger_kernel.ops.sparsemax")
+    z = torch.from_numpy(np.concatenate([cases.planted_peak_logits(8, seed=31), cases.noise_logits(4, 32, 0.2),
+                                         cases.noise_logits(4, 33, 1.0)])).cuda()
+    _, merged = _ops().decode(z, input_is_logits=True, temperature=0.5, return_heatmaps=True)
+    want = liger.LigerSparsemaxFunction.apply((z / 0.5).reshape(-1, 64 * 48).contiguous(), -1).reshape(z.shape)
+    torch.testing.assert_close(merged, want.clamp(0, 1), rtol=0, atol=2e-6)
+    s = merged.flatten(2).sum(-1)
+    torch.testing.assert_close(s, torch.ones_like(s), rtol=0, atol=1e-4)
