@@ -150,6 +150,42 @@ struct OverflowRegistration {
 static OverflowRegistration overflow_registration_;
 }  // namespace
 
+// ---- packed fp32 pairs (sm_100: two IEEE fp32 operations per issue slot) ---------------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t bc2(float c) { return pk2(c, c); }
+
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {  // {lo, hi} -> f16x2, clamped to +-65504
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+
 __device__ __forceinline__ __half sat_half(float v) {
   note_overflow(v);
   return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
@@ -177,15 +213,20 @@ __device__ __forceinline__ void store_operand(void* base, int64_t row, int col, 
 template <int PREC>
 __device__ __forceinline__ void store_operand4(void* base, int64_t row, int col, int k, float4 v) {
   if constexpr (PREC == PP_PREC_FP16X3) {
+    // hi = rn16(sat(64 v)), lo = rn16(64 v - hi), on packed pairs: the same bits as store_operand element by element
+    // (cvt.rn.satfinite clamps to +-65504 like sat_half; the residue is exact in fp32)
     __half* p = reinterpret_cast<__half*>(base) + row * (2 * (int64_t)k);
-    v.x *= kOpScale; v.y *= kOpScale; v.z *= kOpScale; v.w *= kOpScale;
-    __half h0 = sat_half(v.x), h1 = sat_half(v.y), h2 = sat_half(v.z), h3 = sat_half(v.w);
-    __half2 a = __halves2half2(h0, h1), b = __halves2half2(h2, h3);
-    __half2 c = __floats2half2_rn(v.x - __half2float(h0), v.y - __half2float(h1));
-    __half2 d = __floats2half2_rn(v.z - __half2float(h2), v.w - __half2float(h3));
+    const uint64_t v01 = mul2(pk2(v.x, v.y), bc2(kOpScale)), v23 = mul2(pk2(v.z, v.w), bc2(kOpScale));
+    upk2(v01, v.x, v.y); upk2(v23, v.z, v.w);
+    note_overflow4(v.x, v.y, v.z, v.w);
     uint2 hi, lo;
-    hi.x = *reinterpret_cast<uint32_t*>(&a); hi.y = *reinterpret_cast<uint32_t*>(&b);
-    lo.x = *reinterpret_cast<uint32_t*>(&c); lo.y = *reinterpret_cast<uint32_t*>(&d);
+    hi.x = pack_half2_sat(v.x, v.y); hi.y = pack_half2_sat(v.z, v.w);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+    float r0, r1, r2, r3;
+    upk2(sub2(v01, pk2(f0.x, f0.y)), r0, r1);
+    upk2(sub2(v23, pk2(f1.x, f1.y)), r2, r3);
+    const __half2 l0 = __floats2half2_rn(r0, r1), l1 = __floats2half2_rn(r2, r3);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l0); lo.y = *reinterpret_cast<const uint32_t*>(&l1);
     *reinterpret_cast<uint2*>(p + col) = hi;
     *reinterpret_cast<uint2*>(p + k + col) = lo;
   } else if constexpr (PREC == PP_PREC_BF16) {

@@ -114,29 +114,6 @@ __device__ __forceinline__ float gelu_fast(float v) {
 // 128 x 256 tile); the polynomial, the exponent argument and the final blend take 12 packed instructions per PAIR
 // instead of 12 per element.  Same operation order as gelu_fast, lane for lane (the polynomial carries the sign
 // of -p in its coefficients; |h| erf = h copysign(erf, v)): bit-identical results.
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t bc2(float c) { return pk2(c, c); }
-
 // (x0, x1) <- OUT_SCALE * gelu(x * sc + sh) for two neighbouring columns
 template <int OUT_SCALE>
 __device__ __forceinline__ void affine_gelu2(float& x0, float& x1, uint64_t sc, uint64_t sh) {
@@ -177,12 +154,6 @@ __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
-}
-
-__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {  // {lo, hi} -> f16x2, clamped to +-65504
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
 }
 
 // Four consecutive columns of one operand row (col % 4 == 0), see common.cuh "GEMM operand formats";

@@ -5,6 +5,7 @@
 // VisionTransformer / MultiheadAttention (config :56-67), mmcv PatchEmbed (in-tree twin
 // mmpose/models/utils/transformer.py:153-245), flipped pass topdown.py:109-112.
 #include "engine_ops.cuh"
+#include "ln_row.cuh"
 
 #include <math.h>
 
@@ -191,17 +192,8 @@ int launch_patchify(int prec, const PatchifyParams& p, void* a_op, cudaStream_t 
 }
 
 // ---- LayerNorm ----------------------------------------------------------------------------
-// One warp per row; the row lives in registers (NV float4 per lane, d = 128 * NV).
-// Two-pass mean / variance in fp32 like ATen's CPU and CUDA kernels.
-// pad_gw > 0: the operand output is a shared-border (pad_gh + 1) x (pad_gw + 1) map per image (epilogue.cuh pad_geom
-// mode 2: the tap operand of the head's implicit-GEMM convolutions); token (y, x) lands at (y + 1, x).
-__device__ __forceinline__ int64_t padded_row(int64_t row, int gh, int gw) {
-  const int tokens = gh * gw;
-  const int64_t b = row / tokens;
-  const int t = (int)(row % tokens);
-  return (b * (gh + 1) + t / gw + 1) * (gw + 1) + t % gw;
-}
-
+// One warp per row (ln_row.cuh: the same routine finishes rows inside the tcgen05 GEMM epilogue when the LayerNorm
+// is fused into the GEMM that produces its input).
 template <int PREC, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int64_t rows,
@@ -214,34 +206,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * D);
   float4 v[NV];
-  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-  const int64_t op_row = pad_gw > 0 ? padded_row(row, pad_gh, pad_gw) : row;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int col = (lane + 32 * i) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-    const float4 b = *reinterpret_cast<const float4*>(beta + col);
-    float4 o;
-    o.x = (v[i].x - mean) * rstd * g.x + b.x;
-    o.y = (v[i].y - mean) * rstd * g.y + b.y;
-    o.z = (v[i].z - mean) * rstd * g.z + b.z;
-    o.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (out_op) store_operand4<PREC>(out_op, op_row, col, D, o);
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * D + col) = o;
-  }
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  LnParams p;
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.out_op = out_op; p.out_f32 = out_f32; p.pad_gh = pad_gh; p.pad_gw = pad_gw;
+  ln_finish_row<PREC, NV>(v, p, row, lane);
 }
 
 int launch_layernorm(int prec, const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,

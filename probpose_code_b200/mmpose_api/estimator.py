@@ -143,8 +143,13 @@ class TopdownPoseEstimator(nn.Module):
                 return None
             n, shape = len(inputs), inputs[0].shape
             host, dev_buf, _ = self._staging(n, shape, self._rec_shape(), device)
-            for i, t in enumerate(inputs):
-                host[i].copy_(t)
+            step = max(1, (n + 3) // 4)  # quarters: the upload of one runs under the host gather of the next
+            for lo in range(0, n, step):
+                hi = min(n, lo + step)
+                for i in range(lo, hi):
+                    host[i].copy_(inputs[i])
+                dev_buf[lo:hi].copy_(host[lo:hi], non_blocking=True)
+            return dev_buf[:n]
         dev_buf[:n].copy_(host[:n], non_blocking=True)
         return dev_buf[:n]
 
@@ -230,21 +235,39 @@ class TopdownPoseEstimator(nn.Module):
         if getattr(self, "_guard_engine", None) is not eng or self._calls % 256 == 0:
             eng.raise_on_overflow()
             self._guard_engine = eng
+        host = None
         if pinned_records and self._stage is not None and self._stage[2].shape[0] >= records.shape[0]:
             host = self._stage[2][:records.shape[0]]
-            host.copy_(records, non_blocking=True)
-            torch.cuda.current_stream(records.device).synchronize()
-            records = host
+            host.copy_(records, non_blocking=True)  # queued behind the decode kernel; waited for below
         fields = [PixelData(heatmaps=hm) for hm in heatmaps] if want_hm else None
         if cfg.get("output_keypoint_indices", None) is not None:
+            if host is not None:
+                torch.cuda.current_stream(records.device).synchronize()
+                records = host
             return self.add_pred_to_datasample(self.head.pack_records(records), fields, data_samples)
-        # topdown.py:165-167 for the whole batch at once (same float arithmetic per element as the per-person loop)
-        meta = [d.metainfo for d in data_samples]
-        size = np.stack([m["input_size"] for m in meta])[:, None]
-        scale = np.stack([m["input_scale"] for m in meta])[:, None]
-        center = np.stack([m["input_center"] for m in meta])[:, None]
-        preds = self.head.pack_records(records, to_image=lambda k: k / size * scale + center - 0.5 * scale)
-        return self.add_pred_to_datasample(preds, fields, data_samples, mapped=True)
+        # The device is busy for milliseconds: build everything that does not need the results now - the per-person
+        # containers (views of fresh batch arrays), the bbox fields, the geometry of topdown.py:165-167 - and only
+        # then wait for the records and fill the batch arrays in place.
+        arrays, preds = self.head.alloc_records(records.shape[0])
+        self.add_pred_to_datasample(preds, fields, data_samples, mapped=True)
+        geo = np.concatenate([a for d in data_samples for m in (d.metainfo,)
+                              for a in (m["input_size"], m["input_scale"], m["input_center"])]).reshape(-1, 3, 2)
+        # float64 copies (exact; the keypoints are float64) repeated per keypoint: rows of 2 K numbers keep numpy out
+        # of its length-2 inner loops and casting buffers after the device has finished
+        kk = self.head.out_channels
+        half = np.tile((0.5 * geo[:, 1]).astype(np.float64), kk)
+        size, scale, center = (np.tile(geo[:, i].astype(np.float64), kk) for i in range(3))
+
+        def to_image(k):  # topdown.py:165-167 for the whole batch at once (same float arithmetic per element)
+            return (k.reshape(k.shape[0], -1) / size * scale + center - half).reshape(k.shape)
+
+        if host is not None:
+            torch.cuda.current_stream(records.device).synchronize()
+            rec = host.numpy()
+        else:
+            rec = records.detach().cpu().numpy()
+        self.head.fill_records(arrays, rec, to_image=to_image)
+        return data_samples
 
     def add_pred_to_datasample(self, batch_pred_instances: list, batch_pred_fields: Optional[list],
                                batch_data_samples: list, mapped: bool = False) -> list:

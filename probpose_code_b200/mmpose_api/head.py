@@ -14,7 +14,7 @@ from torch import nn
 from .. import ops
 from ._engine_cache import EngineCache
 from .registry import KEYPOINT_CODECS, MODELS, register
-from .structures import InstanceData, PixelData
+from .structures import InstanceData, PixelData, instance_data
 
 
 class BaseHead(nn.Module):
@@ -56,6 +56,19 @@ def _scalar_branch(cin: int, cout: int, last: nn.Module) -> nn.Sequential:
         mods += [nn.Conv2d(cin, cin, 3, 1, 1), nn.BatchNorm2d(cin), nn.MaxPool2d(ks, ks), nn.ReLU(inplace=True)]
     mods += [nn.Conv2d(cin, cout, 1, 1, 0), last]
     return nn.Sequential(*mods)
+
+
+_XY_COLS: dict = {}
+
+
+def _record_xy(rec: np.ndarray) -> np.ndarray:
+    """(B, K, F) records -> contiguous (B, K, 2) locations: one gather along the rows instead of a strided copy with
+    numpy's inner loop over two elements (host time after the device has finished)."""
+    b, k, f = rec.shape
+    cols = _XY_COLS.get((k, f))
+    if cols is None:
+        cols = _XY_COLS[(k, f)] = (np.arange(k)[:, None] * f + np.arange(2)).reshape(-1)
+    return np.take(rec.reshape(b, k * f), cols, axis=1).reshape(b, k, 2)
 
 
 @register(MODELS, ["ProbMapHead"])
@@ -158,25 +171,44 @@ class ProbMapHead(BaseHead):
     def forward_heatmap(self, x: torch.Tensor) -> torch.Tensor:
         return self.forward((x,))[0]
 
-    def pack_records(self, records: torch.Tensor, to_image=None) -> List[InstanceData]:
-        """Device records (B, K, 7) -> the reference's per-person ``InstanceData``
-        (probmap_head.py:776-798), with ONE device->host copy for the batch.  ``to_image``: optional callable
-        mapping the whole batch's input-space keypoints (B, K, 2) to image space in one vectorised step (the
-        estimator's topdown.py:165-167 arithmetic); the per-person arrays are views of the batch arrays."""
-        rec = records.detach().cpu().numpy()
+    def _codec(self):
         codec = self.decoder
         if codec is None or not hasattr(codec, "keypoints_from_locs"):
             raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__} (ProbMap codec required)")
-        kpts = codec.keypoints_from_locs(rec[:, :, :2])
-        if to_image is not None:
-            kpts = to_image(kpts)
-        cols = np.ascontiguousarray(rec[:, :, 2:].transpose(2, 0, 1))[:, :, None]  # (5, B, 1, K)
+        return codec
+
+    def alloc_records(self, batch: int):
+        """The reference's per-person ``InstanceData`` (probmap_head.py:776-798) for a batch whose records have not
+        arrived yet: fresh batch arrays plus one container per person holding VIEWS of them.  Everything here is host
+        work that needs no result, so the fused path does it while the device is still computing; ``fill_records``
+        then writes the batch arrays in place."""
+        k = self.out_channels
+        kpts = np.empty((batch, 1, k, 2), dtype=np.float64)
+        cols = np.empty((5, batch, 1, k), dtype=np.float32)  # conf, prob, vis, oks, err
         conf, prob, vis, oks, err = cols
         scores = conf if self.freeze_oks else oks  # probmap_head.py:796-798
-        kpts = kpts[:, None]
-        return [InstanceData(keypoints=kpts[i], keypoint_scores=scores[i], keypoints_conf=conf[i], keypoints_probs=prob[i],
-                             keypoints_visible=vis[i], keypoints_oks=oks[i], keypoints_error=err[i])
-                for i in range(rec.shape[0])]
+        preds = [instance_data(keypoints=a, keypoint_scores=s_, keypoints_conf=c, keypoints_probs=p, keypoints_visible=v,
+                               keypoints_oks=o, keypoints_error=e)
+                 for a, s_, c, p, v, o, e in zip(kpts, scores, conf, prob, vis, oks, err)]
+        return (kpts, cols), preds
+
+    def fill_records(self, arrays, rec: np.ndarray, to_image=None) -> None:
+        """Host records (B, K, 7) -> the batch arrays of ``alloc_records``.  ``to_image``: optional callable mapping the
+        whole batch's input-space keypoints (B, K, 2) to image space in one vectorised step (the estimator's
+        topdown.py:165-167 arithmetic)."""
+        kpts, cols = arrays
+        k = self._codec().keypoints_from_locs(_record_xy(rec))
+        kpts[:, 0] = k if to_image is None else to_image(k)
+        cols[:, :, 0] = rec[:, :, 2:].transpose(2, 0, 1)
+
+    def pack_records(self, records: torch.Tensor, to_image=None) -> List[InstanceData]:
+        """Device records (B, K, 7) -> the reference's per-person ``InstanceData`` with ONE device->host copy for the
+        batch; the per-person arrays are views of the batch arrays."""
+        self._codec()
+        rec = records.detach().cpu().numpy()
+        arrays, preds = self.alloc_records(rec.shape[0])
+        self.fill_records(arrays, rec, to_image)
+        return preds
 
     @staticmethod
     def fused_test_cfg(test_cfg: dict) -> bool:
@@ -319,18 +351,33 @@ class HeatmapHead(BaseHead):
         eng = self._cache.get(self.engine_tensors(), x.shape[0], x.device)
         return eng.head(x.float().contiguous())
 
-    def pack_records(self, records: torch.Tensor, to_image=None) -> List[InstanceData]:
-        """Device records (B, K, 3) -> per-person ``InstanceData(keypoints, keypoint_scores)`` (base_head.py:79-84);
-        ``to_image`` as in :meth:`ProbMapHead.pack_records`."""
-        rec = records.detach().cpu().numpy()
+    def _codec(self):
         codec = self.decoder
         if codec is None or not hasattr(codec, "keypoints_from_locs"):
             raise RuntimeError(f"The decoder has not been set in {self.__class__.__name__} (UDPHeatmap codec required)")
-        kpts = codec.keypoints_from_locs(rec[:, :, :2])
-        if to_image is not None:
-            kpts = to_image(kpts)
-        kpts, scores = kpts[:, None], np.ascontiguousarray(rec[:, :, 2])[:, None]
-        return [InstanceData(keypoints=kpts[i], keypoint_scores=scores[i]) for i in range(rec.shape[0])]
+        return codec
+
+    def alloc_records(self, batch: int):
+        """Per-person ``InstanceData(keypoints, keypoint_scores)`` (base_head.py:79-84) as views of fresh batch arrays;
+        see :meth:`ProbMapHead.alloc_records`."""
+        k = self.out_channels
+        kpts = np.empty((batch, 1, k, 2), dtype=np.float64)
+        scores = np.empty((batch, 1, k), dtype=np.float32)
+        return (kpts, scores), [instance_data(keypoints=a, keypoint_scores=s_) for a, s_ in zip(kpts, scores)]
+
+    def fill_records(self, arrays, rec: np.ndarray, to_image=None) -> None:
+        kpts, scores = arrays
+        k = self._codec().keypoints_from_locs(_record_xy(rec))
+        kpts[:, 0] = k if to_image is None else to_image(k)
+        scores[:, 0] = rec[:, :, 2]
+
+    def pack_records(self, records: torch.Tensor, to_image=None) -> List[InstanceData]:
+        """Device records (B, K, 3) -> per-person ``InstanceData``; ``to_image`` as in :meth:`ProbMapHead.fill_records`."""
+        self._codec()
+        rec = records.detach().cpu().numpy()
+        arrays, preds = self.alloc_records(rec.shape[0])
+        self.fill_records(arrays, rec, to_image)
+        return preds
 
     @torch.no_grad()
     def predict(self, feats, batch_data_samples, test_cfg: dict = {}):

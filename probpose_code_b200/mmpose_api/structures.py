@@ -10,11 +10,13 @@ try:
 except Exception:  # noqa: BLE001
 
     class _Data:
+        # one dict per container and no per-field call in the constructor: the fused path builds a batch of these per
+        # call, on the host, after the device has finished (time the GPU cannot hide)
+        __slots__ = ("_fields", "_meta")
+
         def __init__(self, *, metainfo=None, **fields):
-            object.__setattr__(self, "_fields", {})
-            object.__setattr__(self, "_meta", dict(metainfo or {}))
-            for k, v in fields.items():
-                self.set_field(v, k)
+            object.__setattr__(self, "_fields", fields)
+            object.__setattr__(self, "_meta", dict(metainfo) if metainfo else {})
 
         def set_field(self, value, name, **_):
             self._fields[name] = value
@@ -27,11 +29,11 @@ except Exception:  # noqa: BLE001
             return self._meta
 
         def __setattr__(self, name, value):
-            self.set_field(value, name)
+            self._fields[name] = value
 
         def __getattr__(self, name):
             try:
-                return object.__getattribute__(self, "_fields")[name]
+                return self._fields[name]
             except KeyError:
                 raise AttributeError(name) from None
 
@@ -53,9 +55,21 @@ except Exception:  # noqa: BLE001
     class InstanceData(_Data):
         pass
 
+    def _bare(cls, fields: dict):
+        obj = cls.__new__(cls)
+        _Data._fields.__set__(obj, fields)
+        _Data._meta.__set__(obj, {})
+        return obj
+
     class PixelData(_Data):
         pass
 
     class PoseDataSample(_Data):
         """Fields used on this path: ``gt_instances`` (bboxes, bbox_scores), ``pred_instances``,
         ``pred_fields``; metainfo ``input_center / input_scale / input_size / flip_indices``."""
+
+
+def instance_data(**fields) -> "InstanceData":
+    """One ``InstanceData`` from ready-made fields (a batch of them is built per call on the fused path)."""
+    bare = globals().get("_bare")
+    return bare(InstanceData, fields) if bare is not None else InstanceData(**fields)
