@@ -146,8 +146,7 @@ class TopdownPoseEstimator(nn.Module):
             step = max(1, (n + 3) // 4)  # quarters: the upload of one runs under the host gather of the next
             for lo in range(0, n, step):
                 hi = min(n, lo + step)
-                for i in range(lo, hi):
-                    host[i].copy_(inputs[i])
+                torch.stack(inputs[lo:hi], out=host[lo:hi])  # one multi-threaded gather per quarter, straight into pinned memory
                 dev_buf[lo:hi].copy_(host[lo:hi], non_blocking=True)
             return dev_buf[:n]
         dev_buf[:n].copy_(host[:n], non_blocking=True)
