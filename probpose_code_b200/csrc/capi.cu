@@ -10,6 +10,7 @@ namespace pp {
 
 static thread_local char g_error[1024] = "";
 thread_local int64_t g_launch_count = 0;
+thread_local cudaAccessPolicyWindow L2Window::win = {};
 
 bool pdl_enabled() {
   static const bool on = getenv("PP_NO_PDL") == nullptr;

@@ -64,15 +64,42 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 bool pdl_enabled();  // capi.cu: on unless PP_NO_PDL is set in the environment
 
+// ---- L2 residency of the residual stream ----------------------------------------------------
+// The fp32 residual stream x (M x D, 38 MB for 64 crops with the flipped pass) is read and rewritten in place by six
+// kernels of every ViT layer while ~1 GB of other activations streams through the 126 MB L2 between two of its uses, so
+// without help it comes back from HBM every time (proj and the LayerNorms are HBM-bound on exactly these bytes).  The
+// engine marks it PERSISTING: every launch between L2Window::set and ::clear carries an access-policy window over x
+// (a launch attribute, so it works on any stream including the legacy default one and is captured into graph nodes).
+struct L2Window {
+  static thread_local cudaAccessPolicyWindow win;  // num_bytes == 0: none
+  static void set(const void* base, size_t bytes, float hit_ratio) {
+    win.base_ptr = const_cast<void*>(base); win.num_bytes = bytes; win.hitRatio = hit_ratio;
+    win.hitProp = cudaAccessPropertyPersisting; win.missProp = cudaAccessPropertyStreaming;
+  }
+  static void clear() { win.num_bytes = 0; }
+  // appends the window to a launch's attribute list; returns the new count
+  static int attach(cudaLaunchAttribute* attr, int n) {
+    if (win.num_bytes == 0) return n;
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow = win;
+    return n + 1;
+  }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  na = L2Window::attach(attr, na);
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 

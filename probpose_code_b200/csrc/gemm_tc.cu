@@ -625,8 +625,8 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams&
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
+  cudaLaunchAttribute attr[3];
+  int na = L2Window::attach(attr, 0);
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
