@@ -145,21 +145,6 @@ typedef struct pp_gemm_args {
   int32_t out_pad;
   int32_t cta_pair;       /* 0 = auto; 1 = one CTA per 128-row tile; 2 = CTA pairs (tcgen05
                              cta_group::2, 256-row tiles) - tuning / tests                   */
-  /* Fused LayerNorm of the finished output rows: the nn.LayerNorm that follows the patch
-   * embedding, attn.proj and ffn Linear of a ViT layer (mmpretrain TransformerEncoderLayer.ln1 /
-   * ln2, VisionTransformer.ln1) runs inside the GEMM that produces its input.  The epilogue warp
-   * that stores the LAST tile of a 32-row group (counted in ln_counters) re-reads those rows of d
-   * from L2 and normalises them with the arithmetic of the stand-alone kernel (same bits).
-   * Needs a tensor-core precision, PP_OUT_F32, n == ldd == 384 or 768, m % 4 == 0 and the
-   * identity row mapping (no up_*, in_pad, out_pad); ln_gamma == NULL disables.               */
-  const float* ln_gamma;  /* device fp32[n]                                                   */
-  const float* ln_beta;   /* device fp32[n]                                                   */
-  void* ln_out;           /* device operand (m, n) in `precision`, or NULL                    */
-  float* ln_out_f32;      /* device fp32 (m, n), or NULL                                      */
-  int32_t* ln_counters;   /* device int32[(m + 31) / 32]: zero on entry, zero again on return */
-  float ln_eps;
-  int32_t ln_pad_gh, ln_pad_gw; /* ln_pad_gw > 0: ln_out rows go to the interior of a shared-border
-                             (ln_pad_gh + 1) x (ln_pad_gw + 1) map per image (in_pad = 2 layout) */
 } pp_gemm_args;
 
 PP_API int pp_gemm(const pp_gemm_args* args, void* stream);

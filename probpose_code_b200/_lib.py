@@ -46,9 +46,7 @@ class GemmArgs(C.Structure):
                 ("ldd", C.c_int32), ("plane", C.c_int32), ("up_hin", C.c_int32), ("up_win", C.c_int32),
                 ("up_py", C.c_int32), ("up_px", C.c_int32), ("tile_n", C.c_int32), ("res_mod", C.c_int32),
                 ("a_taps", C.c_int32), ("a_tap_shift", C.c_int32 * 9), ("in_pad", C.c_int32), ("in_h", C.c_int32),
-                ("in_w", C.c_int32), ("out_pad", C.c_int32), ("cta_pair", C.c_int32),
-                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_out", C.c_void_p), ("ln_out_f32", C.c_void_p),
-                ("ln_counters", C.c_void_p), ("ln_eps", C.c_float), ("ln_pad_gh", C.c_int32), ("ln_pad_gw", C.c_int32)]
+                ("in_w", C.c_int32), ("out_pad", C.c_int32), ("cta_pair", C.c_int32)]
 
 
 class EngineCfg(C.Structure):

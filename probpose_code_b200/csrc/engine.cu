@@ -73,6 +73,8 @@ struct pp_engine {
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   int graph_max_images = 0;           // replay when passes * batch <= this; 0 = off, < 0 = no limit
   int64_t graph_replays = 0;
+  size_t l2_setaside = 0;  // persisting-L2 carve-out available for the residual stream (0: off)
+  size_t l2_max_window = 0;  // largest access-policy window of the device
   size_t g_stride = 0;  // bytes between the per-branch tap-gather buffers
   bool branches = false;  // ProbMapHead: the four scalar branches exist (HeatmapHead: heatmap stack only)
 
@@ -83,9 +85,7 @@ struct pp_engine {
   size_t w_dc[2][4], dc_scale[2], dc_shift[2], w_final;
   size_t w_c1, w_c2[4], w_c3[4], c_scale[3], c_shift[3], tail_w, tail_b;
   // activations (byte offsets)
-  size_t x, a_op, qkv, h_op, feat_op, feat_f32, ln_cnt;
-  size_t ln_cnt_bytes = 0;
-  bool ln_fuse = false;  // LayerNorms run inside the GEMM that produces their input (tensor-core precisions)
+  size_t x, a_op, qkv, h_op, feat_op, feat_f32;
   size_t feat_bytes = 0, d1_bytes = 0;
   size_t g_op, d1_op, d2_op, logits, c_f32, pool_op, scal, pack_tmp;
 
@@ -205,8 +205,6 @@ static size_t plan(pp_engine* e) {
     e->a_op = b.take(pp_operand_bytes(prec, M, e->PK > D ? e->PK : D));
     e->qkv = b.take((size_t)M * 3 * D * sizeof(float));
     e->h_op = b.take(pp_operand_bytes(prec, M, FF));
-    e->ln_cnt_bytes = (size_t)((M + 31) / 32) * sizeof(int);  // arrival counters of the fused LayerNorm, one per 32 rows
-    e->ln_cnt = b.take(e->ln_cnt_bytes);
   }
   // feat_op and d1_op are shared-border maps (gh + 1) x (gw + 1) / (2 gh + 1) x (2 gw + 1) (epilogue.cuh pad_geom mode 2): the tap
   // operands of the head's implicit-GEMM deconvolutions / 3x3 convolution (borders zeroed in finalize)
@@ -313,10 +311,6 @@ static int to_operand(const pp_engine* e, const float* src, int64_t rows, int64_
   return pp_operand_from_f32(e->prec, src, rows, k, k, e->at<>(dst_off), st);
 }
 
-// The patch matrix (M, PK).  With the fused LayerNorm the patch-embedding GEMM writes ln1(x) into a_op while other
-// CTAs still read patch rows, so the patch matrix lives in h_op (free until the first fc1) when that is large enough.
-static size_t patch_buf(const pp_engine* e) { return (e->ln_fuse && e->FF >= e->PK) ? e->h_op : e->a_op; }
-
 // ---- forward pieces ---------------------------------------------------------------------------
 // crops -> patch matrix (the only kernel of the backbone that reads caller memory)
 static int run_patchify(pp_engine* e, const uint8_t* u8, const float* xf, int batch, int passes, cudaStream_t st) {
@@ -326,52 +320,40 @@ static int run_patchify(pp_engine* e, const uint8_t* u8, const float* xf, int ba
   pp_.img_h = e->cfg.img_h; pp_.img_w = e->cfg.img_w; pp_.patch = e->cfg.patch; pp_.pad = e->cfg.patch_pad;
   pp_.gh = e->gh; pp_.gw = e->gw;
   for (int c = 0; c < 3; ++c) { pp_.mean[c] = e->cfg.mean[c]; pp_.inv_std[c] = 1.0f / e->cfg.std[c]; }
-  return timed(e, PP_KC_OTHER, st, [&] { return launch_patchify(prec, pp_, e->at<>(patch_buf(e)), st); });
+  return timed(e, PP_KC_OTHER, st, [&] { return launch_patchify(prec, pp_, e->at<>(e->a_op), st); });
 }
 
-// patch matrix -> features: workspace buffers only
+static int run_encoder_layers(pp_engine* e, int batch, int passes, bool want_f32, cudaStream_t st);
+
+// patch matrix -> features.  The residual stream stays resident in L2 for the whole encoder (common.cuh L2Window);
+// when it is larger than the carve-out, the fraction that fits.
 static int run_encoder(pp_engine* e, int batch, int passes, bool want_f32, cudaStream_t st) {
+  const size_t x_bytes = (size_t)passes * batch * e->tokens * e->D * sizeof(float);
+  if (e->l2_setaside > 0 && x_bytes > 0) {
+    const size_t win = x_bytes < e->l2_max_window ? x_bytes : e->l2_max_window;
+    L2Window::set(e->at<>(e->x), win, win <= e->l2_setaside ? 1.0f : (float)((double)e->l2_setaside / (double)win));
+  }
+  const int rc = run_encoder_layers(e, batch, passes, want_f32, st);
+  L2Window::clear();
+  return rc;
+}
+
+static int run_encoder_layers(pp_engine* e, int batch, int passes, bool want_f32, cudaStream_t st) {
   const int D = e->D, FF = e->FF, prec = e->prec;
   const int64_t M = (int64_t)passes * batch * e->tokens;
-  float* x = e->at<float>(e->x);
-  // LayerNorm l (0 .. depth - 1: ln1 of layer l; depth: the final backbone.ln1) of the residual stream.  Fused: it
-  // rides on the GEMM that completes x (pp_gemm_args::ln_*); otherwise a launch of its own.
-  auto ln_names = [&](int l, bool second, const float*& gamma, const float*& beta) {
-    if (l >= e->depth) { gamma = e->P("backbone.ln1.weight"); beta = e->P("backbone.ln1.bias"); return; }
-    const std::string p = "backbone.layers." + std::to_string(l) + (second ? ".ln2." : ".ln1.");
-    gamma = e->P(p + "weight"); beta = e->P(p + "bias");
-  };
-  auto ln_fused = [&](pp_gemm_args& g, int l, bool second) {
-    ln_names(l, second, g.ln_gamma, g.ln_beta);
-    g.ln_eps = e->cfg.ln_eps; g.ln_counters = e->at<int>(e->ln_cnt);
-    if (l >= e->depth) {
-      g.ln_out = e->at<>(e->feat_op); g.ln_out_f32 = want_f32 ? e->at<float>(e->feat_f32) : nullptr;
-      g.ln_pad_gh = e->gh; g.ln_pad_gw = e->gw;
-    } else {
-      g.ln_out = e->at<>(e->a_op);
-    }
-  };
-  auto ln_launch = [&](int l, bool second) {
-    const float *gamma, *beta;
-    ln_names(l, second, gamma, beta);
-    if (l >= e->depth)
-      return timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, gamma, beta, e->cfg.ln_eps, M, D, e->at<>(e->feat_op),
-                                                                     want_f32 ? e->at<float>(e->feat_f32) : nullptr, st, e->gh, e->gw); });
-    return timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, gamma, beta, e->cfg.ln_eps, M, D, e->at<>(e->a_op), nullptr, st); });
-  };
   {
-    pp_gemm_args g = gemm_args(e, M, D, e->PK, e->at<>(patch_buf(e)), e->at<>(e->w_patch));
+    pp_gemm_args g = gemm_args(e, M, D, e->PK, e->at<>(e->a_op), e->at<>(e->w_patch));
     g.shift = e->P("backbone.patch_embed.projection.bias");
     g.residual = e->P("backbone.pos_embed"); g.res_mod = e->tokens;
-    g.d = x;
-    const bool fuse = e->ln_fuse && patch_buf(e) != e->a_op;
-    if (fuse) ln_fused(g, 0, false);
+    g.d = e->at<>(e->x);
     PP_TRY(gemm(e, g, st));
-    if (!fuse) PP_TRY(ln_launch(0, false));
   }
+  float* x = e->at<float>(e->x);
   for (int l = 0; l < e->depth; ++l) {
     const std::string p = "backbone.layers." + std::to_string(l) + ".";
     const pp_engine::Layer& L = e->layers[l];
+    PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P(p + "ln1.weight"), e->P(p + "ln1.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
+                            nullptr, st); }));
     pp_gemm_args g = gemm_args(e, M, 3 * D, D, e->at<>(e->a_op), e->at<>(L.wqkv));
     g.shift = e->P(p + "attn.qkv.bias"); g.d = e->at<>(e->qkv);
     const bool tc_attn = prec != PP_PREC_FP32_SIMT;  // q, k, v leave the GEMM pre-split for the tensor-core attention
@@ -381,23 +363,21 @@ static int run_encoder(pp_engine* e, int batch, int passes, bool want_f32, cudaS
       return tc_attn ? (attention_use_tc() ? launch_attention_tc : launch_attention_mma)(prec, e->at<>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st)
                      : launch_attention(prec, e->at<float>(e->qkv), passes * batch, e->tokens, e->heads, e->dh, e->at<>(e->a_op), st);
     }));
-    // proj reads a_op (attention output) and, fused, writes ln2(x) over the same rows: a 32-row group is only
-    // normalised after every tile of its rows has been stored, i.e. after the last read of those operand rows
     g = gemm_args(e, M, D, D, e->at<>(e->a_op), e->at<>(L.wproj));
     g.shift = e->P(p + "attn.proj.bias"); g.residual = x; g.d = x;
-    if (e->ln_fuse) ln_fused(g, l, true);
     PP_TRY(gemm(e, g, st));
-    if (!e->ln_fuse) PP_TRY(ln_launch(l, true));
+    PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P(p + "ln2.weight"), e->P(p + "ln2.bias"), e->cfg.ln_eps, M, D, e->at<>(e->a_op),
+                            nullptr, st); }));
     g = gemm_args(e, M, FF, D, e->at<>(e->a_op), e->at<>(L.wfc1));
     g.shift = e->P(p + "ffn.layers.0.0.bias"); g.act = PP_ACT_GELU; g.out_kind = PP_OUT_OPERAND; g.ldd = FF;
     g.d = e->at<>(e->h_op);
     PP_TRY(gemm(e, g, st));
     g = gemm_args(e, M, D, FF, e->at<>(e->h_op), e->at<>(L.wfc2));
     g.shift = e->P(p + "ffn.layers.1.bias"); g.residual = x; g.d = x;
-    if (e->ln_fuse) ln_fused(g, l + 1, false);  // ln1 of the next layer, or the final LayerNorm
     PP_TRY(gemm(e, g, st));
-    if (!e->ln_fuse) PP_TRY(ln_launch(l + 1, false));
   }
+  PP_TRY(timed(e, PP_KC_OTHER, st, [&] { return launch_layernorm(prec, x, e->P("backbone.ln1.weight"), e->P("backbone.ln1.bias"), e->cfg.ln_eps, M, D,
+                          e->at<>(e->feat_op), want_f32 ? e->at<float>(e->feat_f32) : nullptr, st, e->gh, e->gw); }));
   return PP_OK;
 }
 
@@ -593,7 +573,24 @@ extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_
       return PP_ERR_CUDA;
     }
   }
-  e->ln_fuse = e->depth > 0 && e->prec != PP_PREC_FP32_SIMT && getenv("PP_NO_LN_FUSE") == nullptr;
+  if (e->depth > 0 && getenv("PP_NO_L2_PERSIST") == nullptr) {
+    // L2 carve-out for the residual stream (a device-wide limit: the largest request of the engines of a process wins)
+    int dev = 0, max_persist = 0, max_window = 0;
+    size_t cur = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess && max_persist > 0 &&
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess && max_window > 0) {
+      const size_t x_max = (size_t)e->max_b2 * e->tokens * e->D * sizeof(float);
+      size_t want = x_max < (size_t)max_persist ? x_max : (size_t)max_persist;
+      const char* frac = getenv("PP_L2_PERSIST_MB");
+      if (frac) want = (size_t)atoi(frac) << 20 < (size_t)max_persist ? (size_t)atoi(frac) << 20 : (size_t)max_persist;
+      if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) cur = 0;
+      if (want > cur && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) cur = want;
+      e->l2_setaside = cur < want ? cur : want;
+      e->l2_max_window = (size_t)max_window;
+    }
+    cudaGetLastError();  // an unsupported limit is not an error of the engine
+  }
   {  // graph replay of small calls is on by default; PP_ENGINE_GRAPH = 0 (off), -1 (every size) or a limit in images
     const char* env = getenv("PP_ENGINE_GRAPH");
     e->graph_max_images = env ? atoi(env) : kGraphDefaultMaxImages;
@@ -656,7 +653,6 @@ extern "C" int pp_engine_finalize(pp_engine* e, void* stream) {
                g ? "head" : "backbone", missing[g]->name.c_str());
   PP_REQUIRE(loaded[0] + loaded[1] > 0, PP_ERR_STATE, "pp_engine_finalize: no parameters loaded");
   PP_CHECK_CUDA(cudaMemsetAsync(e->at<>(e->feat_op), 0, e->feat_bytes, st));  // zero border of the padded feature map
-  if (e->ln_cnt_bytes) PP_CHECK_CUDA(cudaMemsetAsync(e->at<>(e->ln_cnt), 0, e->ln_cnt_bytes, st));  // every launch leaves them zero again
   const int D = e->D, FF = e->FF, DC = e->DC, K = e->K;
   if (total[0] > 0 && loaded[0] == total[0]) {
     PP_TRY(to_operand(e, e->P("backbone.patch_embed.projection.weight"), D, e->PK, e->w_patch, st));

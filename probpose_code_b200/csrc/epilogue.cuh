@@ -17,15 +17,6 @@ struct EpiParams {
   int up_hin, up_py, up_px;        // up_hin != 0: stride-2 ConvTranspose2d phase scatter
   int in_h, in_w, in_pad, out_pad;  // geometry of the map the GEMM rows enumerate (see map_out_row)
   int res_mod;
-  // fused LayerNorm of the finished rows (gemm_tc.cu): ln_gamma == nullptr disables
-  const float* ln_gamma;
-  const float* ln_beta;
-  void* ln_out;
-  float* ln_out_f32;
-  int* ln_counters;
-  float ln_eps;
-  int ln_pad_gh, ln_pad_gw;
-  int ln_debug;  // TEMP experiment knob
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

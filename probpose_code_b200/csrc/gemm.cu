@@ -99,17 +99,6 @@ int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st) {
   e.in_h = a.in_pad ? a.in_h : a.up_hin; e.in_w = a.in_pad ? a.in_w : a.up_win;
   if (a.out_pad && !a.in_pad && !a.up_hin) { e.in_h = a.in_h; e.in_w = a.in_w; }
   e.res_mod = a.res_mod;
-  e.ln_gamma = a.ln_gamma; e.ln_beta = a.ln_beta; e.ln_out = a.ln_out; e.ln_out_f32 = a.ln_out_f32;
-  e.ln_counters = a.ln_counters; e.ln_eps = a.ln_eps; e.ln_pad_gh = a.ln_pad_gh; e.ln_pad_gw = a.ln_pad_gw;
-  { static const int dbg = getenv("PP_LN_DEBUG") ? atoi(getenv("PP_LN_DEBUG")) : 0; e.ln_debug = dbg; }
-  if (a.ln_gamma != nullptr) {
-    PP_REQUIRE(a.precision != PP_PREC_FP32_SIMT && a.out_kind == PP_OUT_F32 && a.n == a.ldd && (a.n == 384 || a.n == 768) &&
-                   !a.up_hin && !a.in_pad && !a.out_pad && a.m % 4 == 0,
-               PP_ERR_UNSUPPORTED, "pp_gemm: the fused LayerNorm needs a tensor-core precision, PP_OUT_F32, n == ldd in {384, 768}, "
-               "m %% 4 == 0 and the identity row mapping (m=%d n=%d ldd=%d out_kind=%d)", a.m, a.n, a.ldd, a.out_kind);
-    PP_REQUIRE(a.ln_beta != nullptr && a.ln_counters != nullptr && (a.ln_out != nullptr || a.ln_out_f32 != nullptr), PP_ERR_INVALID,
-               "pp_gemm: the fused LayerNorm needs ln_beta, ln_counters and at least one of ln_out / ln_out_f32");
-  }
   if (a.precision == PP_PREC_FP32_SIMT) {
     SimtTaps tp = {};
     tp.taps = a.a_taps > 1 ? a.a_taps : 1;

@@ -31,7 +31,6 @@
 
 #include "common.cuh"
 #include "epilogue.cuh"
-#include "ln_row.cuh"
 #include "ptx.cuh"
 
 namespace pp {
@@ -83,7 +82,7 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kStagingBytes + MISC_BYTES + 1024;
   static_assert(STAGES >= 2, "tile too large for a 2-stage ring");
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
-  static_assert((2 * STAGES + 4) * 8 + 16 + kEpiWarps * 4 <= MISC_BYTES, "barrier block too small");
+  static_assert((2 * STAGES + 4) * 8 + 16 <= MISC_BYTES, "barrier block too small");
   static_assert(BN % 32 == 0, "epilogue works on 32-column chunks");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must keep the swizzle alignment");
   static_assert(!PAIR || BN % 32 == 0, "pair tiles split W in two halves of whole 16-row groups");
@@ -191,73 +190,6 @@ __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int
   }
 }
 
-// ---- fused LayerNorm (EpiParams::ln_*) -------------------------------------------------------
-// A 32-row group of the fp32 output is complete once every tile holding a piece of it has been stored and released
-// (arrival counter, see the epilogue).  Normalising it is ~8 K dependent warp instructions - far too long for the
-// one warp that happens to arrive last (measured: +50 us per GEMM) - so the group becomes a JOB of kLnUnits units of
-// kLnUnitRows rows in a CTA-local queue (one 32-bit slot per epilogue warp: group << 4 | next unit), and every
-// epilogue warp of the CTA takes units while it would otherwise spin on the next accumulator (the epilogue warps of
-// the LayerNorm-carrying GEMMs - proj, fc2 - are idle most of the time), and drains the queue before it exits.
-constexpr int kLnUnitRows = 4;
-constexpr int kLnUnits = 32 / kLnUnitRows;
-constexpr int kLnSlotBytes = kEpiWarps * 4;
-
-struct LnJob {  // what a unit needs, passed by value (ln_poll is a real call: one copy of the code per kernel)
-  LnParams p;
-  const float* x;
-  int m, n, dbg;
-};
-__device__ __forceinline__ LnJob ln_job(const EpiParams& e) {
-  LnJob j;
-  j.p.gamma = e.ln_gamma; j.p.beta = e.ln_beta; j.p.eps = e.ln_eps; j.p.out_op = e.ln_out; j.p.out_f32 = e.ln_out_f32;
-  j.p.pad_gh = e.ln_pad_gh; j.p.pad_gw = e.ln_pad_gw;
-  j.x = reinterpret_cast<const float*>(e.d); j.m = e.m; j.n = e.n; j.dbg = e.ln_debug;
-  return j;
-}
-
-// Rows [row0, row0 + kLnUnitRows): R rows at a time are pulled from L2 (ld.global.cg: other SMs wrote them, and this
-// SM's L1 may still hold the residual it read from the same addresses), then normalised by ln_finish_row, the
-// routine of the stand-alone kernel (same bits).
-template <int PREC, int NV, int R>
-__device__ __forceinline__ void ln_finish_rows(const LnJob& j, int row0, int lane) {
-  constexpr int D = NV * 128;
-#pragma unroll 1
-  for (int r0 = 0; r0 < kLnUnitRows; r0 += R) {
-    float4 v[R][NV];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t row = row0 + r0 + r;
-      const float4* xr = reinterpret_cast<const float4*>(j.x + row * D);
-#pragma unroll
-      for (int i = 0; i < NV; ++i) v[r][i] = __ldcg(xr + lane + 32 * i);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) ln_finish_row<PREC, NV>(v[r], j.p, row0 + r0 + r, lane);
-  }
-}
-
-// Take one unit from the CTA's queue and finish it.  False: the queue is empty.  (True also when the claim lost a
-// race - the caller polls again.)  The whole warp calls this converged.
-template <int PREC>
-__device__ __noinline__ bool ln_poll(const LnJob j, uint32_t* slots, int lane) {
-  uint32_t word = kLnUnits;
-  if (lane < kEpiWarps) word = *reinterpret_cast<volatile uint32_t*>(slots + lane);
-  const uint32_t avail = __ballot_sync(0xffffffffu, (word & 15u) < (uint32_t)kLnUnits);
-  if (avail == 0) return false;
-  const int src = __ffs(avail) - 1;
-  uint32_t got = 0xffffffffu;
-  if (lane == src && atomicCAS(slots + src, word, word + 1u) == word) got = word;
-  got = __shfl_sync(0xffffffffu, got, src);
-  if (got == 0xffffffffu) return true;
-  __threadfence_block();  // the publisher's acquire of the rows (gpu scope) happened before it wrote the slot
-  const int row0 = (int)(got >> 4) * 32 + (int)(got & 15u) * kLnUnitRows;
-  if (j.dbg & 1) return true;
-  if (row0 >= j.m) return true;  // m is a multiple of kLnUnitRows: units are whole or empty
-  if (j.n == 384) ln_finish_rows<PREC, 3, 4>(j, row0, lane);
-  else ln_finish_rows<PREC, 6, 2>(j, row0, lane);
-  return true;
-}
-
 // num_m_tiles counts 128-row tiles (PAIR: 256-row pair tiles); gridDim.x CTAs (PAIR: an even number,
 // launched as clusters of 2) walk them persistently.
 template <int BN, int SPLIT, bool BF16, int OUT, int ACCS, bool PAIR>
@@ -278,7 +210,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint32_t* ln_slots = reinterpret_cast<uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + kStagingBytes + Cfg::MISC_BYTES - kEpiWarps * 4);
 
   auto stage_a = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + part * Cfg::A_BYTES; };
   auto stage_b = [&](int s, int part) { return smem + s * Cfg::STAGE_BYTES + Cfg::NOPS * Cfg::A_BYTES + part * Cfg::B_BYTES; };
@@ -305,7 +236,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       ptx::mbar_init(&tmem_full_bar[s], 1);
       ptx::mbar_init(&tmem_empty_bar[s], PAIR ? 2 * kEpiWarps : kEpiWarps);  // the leader collects both CTAs' epilogues
     }
-    for (int i = 0; i < kEpiWarps; ++i) ln_slots[i] = kLnUnits;  // fused-LayerNorm job slots: exhausted
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -478,23 +408,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           }
         }
       }
-      if constexpr (OUT == PP_OUT_F32) {
-        if (e.ln_gamma != nullptr) {  // fused LayerNorm: finish queued rows instead of spinning on the accumulator
-          uint32_t spins = 0;
-          uint64_t t0 = 0;
-          for (;;) {
-            uint32_t ready = 0;
-            if (lane == 0) ready = ptx::mbar_test_wait(&tmem_full_bar[as], aph);
-            if (__shfl_sync(0xffffffffu, ready, 0)) break;
-            if (!ln_poll<PREC>(ln_job(e), ln_slots, lane) && (++spins & 0xffff) == 0) {  // bounded like ptx::mbar_wait
-              uint64_t t1;
-              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-              if (t0 == 0) t0 = t1;
-              if (t1 - t0 > 2000000000ull) __trap();
-            }
-          }
-        }
-      }
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tcgen05_fence_after();
       const uint32_t tacc = tmem_base + as * Cfg::ACC_COLS + lane_off;
@@ -627,34 +540,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         __syncwarp();
         if (lane == 0) { if constexpr (PAIR) ptx::mbar_arrive_leader(&tmem_empty_bar[as]); else ptx::mbar_arrive(&tmem_empty_bar[as]); }
       }
-      if constexpr (OUT == PP_OUT_F32) {
-        if (e.ln_gamma != nullptr && row_base < e.m) {
-          // Fused LayerNorm.  This warp's part of the tile is stored: release it (fence, then one relaxed arrival per
-          // warp on the counter of its 32-row group).  Two warps share a group, and every n tile of the row block
-          // arrives once, from whichever CTAs run them; the warp that brings the count to 2 x num_n_tiles sees the
-          // whole rows (fence after the arrival) and queues them for this CTA's epilogue warps (ln_poll).  It also
-          // re-arms the counter: nobody else touches it before the next launch.
-          if (!(e.ln_debug & 2)) __threadfence();
-          __syncwarp();
-          int last = 0;
-          if (lane == 0) last = atomicAdd(e.ln_counters + (row_base >> 5), 1) == 2 * num_n_tiles - 1;
-          last = __shfl_sync(0xffffffffu, last, 0);
-          if (last) {
-            if (lane == 0) e.ln_counters[row_base >> 5] = 0;
-            __threadfence();
-            // publish the group in this warp's slot (the previous job of the slot must have been handed out)
-            while ((*reinterpret_cast<volatile uint32_t*>(ln_slots + ew) & 15u) < (uint32_t)kLnUnits) ln_poll<PREC>(ln_job(e), ln_slots, lane);
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(ln_slots + ew) = (uint32_t)(row_base >> 5) << 4;
-            __syncwarp();
-          }
-        }
-      }
-    }
-    if constexpr (OUT == PP_OUT_F32) {
-      if (e.ln_gamma != nullptr) {  // no more tiles: finish what is still queued in this CTA (later jobs are drained by their publishers)
-        while (ln_poll<PREC>(ln_job(e), ln_slots, lane)) {}
-      }
     }
   }
 
@@ -740,8 +625,8 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams&
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
+  cudaLaunchAttribute attr[3];
+  int na = L2Window::attach(attr, 0);
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;

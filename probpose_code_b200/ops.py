@@ -113,18 +113,14 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
          residual: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE, out_kind: int = _lib.OUT_F32,
          out: Optional[torch.Tensor] = None, ldd: Optional[int] = None, plane: int = 0, up=None, tile_n: int = 0,
          res_mod: int = 0, taps: Optional[Sequence[int]] = None, in_pad=None, out_pad: bool = False,
-         out_rows: Optional[int] = None, cta_pair: int = 0, shared_border: bool = False, ln: Optional[dict] = None):
+         out_rows: Optional[int] = None, cta_pair: int = 0, shared_border: bool = False):
     """``pp_gemm``: D = epilogue(A . W^T).  ``a_op`` / ``w_op`` are operand buffers from
     :func:`to_operand`.  Returns the output tensor (fp32, or a uint8 operand buffer).
 
     ``taps``: row shifts of the implicit-GEMM A operand (logical width ``k / len(taps)``);
     ``in_pad=(h, w)``: the A rows enumerate a zero-padded ``(h + 2, w + 2)`` map; ``out_pad``:
     the output map carries a border too; ``shared_border``: both use the ``(h + 1, w + 1)`` layout (``in_pad`` /
-    ``out_pad`` = 2 in the C ABI) instead; ``out_rows``: rows of a freshly allocated output.
-
-    ``ln``: fused LayerNorm of the finished fp32 rows (``pp_gemm_args::ln_*``): ``dict(gamma=, beta=, eps=)`` plus any of
-    ``out_op`` (uint8 operand buffer), ``out_f32`` (fp32 ``(m, n)``), ``pad=(gh, gw)``; buffers that are missing are
-    allocated and the dict is updated in place (``out_op``, ``out_f32``, ``counters``)."""
+    ``out_pad`` = 2 in the C ABI) instead; ``out_rows``: rows of a freshly allocated output."""
     dev = a_op.device
     if out_kind == _lib.OUT_F32:
         ldd = n if ldd is None else ldd
@@ -145,22 +141,10 @@ def gemm(a_op: torch.Tensor, w_op: torch.Tensor, m: int, n: int, k: int, precisi
     ntaps = 0 if taps is None else len(taps)
     shifts = (C.c_int32 * 9)(*([int(t) for t in taps] + [0] * (9 - ntaps))) if taps is not None else (C.c_int32 * 9)()
     ih, iw = in_pad if in_pad is not None else (0, 0)
-    ln_args = (None, None, None, None, None, 0.0, 0, 0)
-    if ln is not None:
-        gh, gw = ln.get("pad", (0, 0))
-        if ln.get("out_op") is None:
-            rows_op = m if gw == 0 else (m // (gh * gw)) * (gh + 1) * (gw + 1)
-            ln["out_op"] = torch.zeros(lib().pp_operand_bytes(precision, rows_op, n), dtype=torch.uint8, device=dev)
-        if ln.get("out_f32") is None and ln.get("want_f32", True):
-            ln["out_f32"] = torch.zeros((m, n), dtype=torch.float32, device=dev)
-        if ln.get("counters") is None:
-            ln["counters"] = torch.zeros(((m + 31) // 32,), dtype=torch.int32, device=dev)
-        ln_args = (ln["gamma"].data_ptr(), ln["beta"].data_ptr(), ln["out_op"].data_ptr(), _ptr(ln.get("out_f32")),
-                   ln["counters"].data_ptr(), float(ln.get("eps", 1e-6)), int(gh), int(gw))
     args = _lib.GemmArgs(precision, m, n, k, a_op.data_ptr(), w_op.data_ptr(), _ptr(scale), _ptr(shift),
                          _ptr(residual), act, out_kind, out.data_ptr(), ldd, plane, hin, win, py, px, tile_n, res_mod,
                          ntaps, shifts, int(in_pad is not None) * (2 if shared_border else 1), ih, iw,
-                         int(bool(out_pad)) * (2 if shared_border else 1), int(cta_pair), *ln_args)
+                         int(bool(out_pad)) * (2 if shared_border else 1), int(cta_pair))
     with torch.cuda.device(dev):
         check(lib().pp_gemm(C.byref(args), _stream()), "pp_gemm")
     return out

@@ -239,26 +239,3 @@ def test_l2_residency_of_the_residual_stream_changes_no_bit(setup, monkeypatch):
         monkeypatch.delenv("PP_NO_L2_PERSIST")
         for flip in (True, False):
             assert torch.equal(on.infer(crops, flip_test=flip), off.infer(crops, flip_test=flip))
-
-
-@pytest.mark.parametrize("batch,flip", [(3, True), (4, False), (40, True)])
-def test_fused_layernorm_engine_is_bit_identical(setup, monkeypatch, batch, flip):
-    """The LayerNorms run inside the GEMMs that produce their input (pp_gemm_args::ln_*); PP_NO_LN_FUSE=1 (read when an
-    engine is created) keeps the 25 stand-alone launches.  Same arithmetic, so the records must agree bit for bit, and
-    the fused engine must launch 25 kernels fewer."""
-    from probpose_code_b200.engine import Engine
-    crops = synth.make_crops(batch, seed=77).cuda()
-    fused = Engine(precision="fp16x3", max_batch=batch).load_state_dict(setup["sd"])
-    fused.set_graph(0)
-    rec_fused = fused.infer(crops, flip_test=flip).cpu()
-    n_fused = fused.last_launch_count
-    monkeypatch.setenv("PP_NO_LN_FUSE", "1")
-    plain = Engine(precision="fp16x3", max_batch=batch).load_state_dict(setup["sd"])
-    monkeypatch.delenv("PP_NO_LN_FUSE")
-    plain.set_graph(0)
-    rec_plain = plain.infer(crops, flip_test=flip).cpu()
-    assert torch.equal(rec_fused, rec_plain)
-    assert plain.last_launch_count - n_fused == 25
-    feat_f = fused.backbone(setup["x"].cuda())
-    feat_p = plain.backbone(setup["x"].cuda())
-    assert torch.equal(feat_f, feat_p)

@@ -212,48 +212,3 @@ def test_cta_pair_gemm(prec, m, n, k, tile_n):
     assert _rel(out, ref + res.double()) <= TOL[prec] * 2
     nxt = ops.gemm(ao, wo, m, n, k, prec, shift=shift, act=_lib.ACT_RELU, out_kind=_lib.OUT_OPERAND, tile_n=tile_n, cta_pair=2)
     assert _rel(_operand_to_f64(nxt, m, n, prec), torch.relu(ref)) <= max(TOL[prec] * 2, {0: 3e-6, 1: 8e-3}[prec])
-
-
-@pytest.mark.parametrize("prec", [_lib.PREC_FP16X3, _lib.PREC_BF16])
-@pytest.mark.parametrize("m,n,k,tile_n,pair", [(24576, 384, 384, 0, 0), (24576, 384, 1536, 0, 0), (1000, 384, 768, 0, 0),
-                                               (2048, 768, 768, 0, 0), (4000, 384, 384, 128, 1), (780, 384, 384, 64, 1),
-                                               (9984, 768, 3072, 0, 0)])
-def test_fused_layernorm(prec, m, n, k, tile_n, pair):
-    """pp_gemm_args::ln_*: the LayerNorm of the finished rows inside the GEMM (the 32-row groups are normalised by
-    whichever epilogue warp stores their last tile, counted across CTAs).  x itself must not change by a bit, the
-    normalised rows must be torch's layer_norm of those x, the operand output must hold exactly the fp32 output, and
-    the counters must be back at zero (the launch re-arms them) - also when the same call is repeated."""
-    ops = _ops()
-    g = torch.Generator(device="cuda").manual_seed(m + k)
-    a, w = torch.randn(m, k, device="cuda", generator=g), torch.randn(n, k, device="cuda", generator=g) * 0.05
-    shift, res = torch.randn(n, device="cuda", generator=g), torch.randn(m, n, device="cuda", generator=g)
-    gamma, beta = torch.rand(n, device="cuda", generator=g) + 0.5, torch.randn(n, device="cuda", generator=g)
-    ao, wo = ops.to_operand(a, prec), ops.to_operand(w, prec)
-    plain = ops.gemm(ao, wo, m, n, k, prec, shift=shift, residual=res, tile_n=tile_n, cta_pair=pair)
-    ln = dict(gamma=gamma, beta=beta, eps=1e-6)
-    for rep in range(3):
-        x = res.clone()  # in place, as the engine runs it: residual and output are the same buffer
-        out = ops.gemm(ao, wo, m, n, k, prec, shift=shift, residual=x, out=x, tile_n=tile_n, cta_pair=pair, ln=ln)
-        assert torch.equal(out, plain), "the fused LayerNorm changed the GEMM output"
-        assert int(ln["counters"].abs().sum()) == 0, "arrival counters not re-armed"
-        ref = torch.nn.functional.layer_norm(plain.double(), (n,), gamma.double(), beta.double(), 1e-6)
-        assert (ln["out_f32"].double() - ref).abs().max().item() <= 2e-5
-        assert torch.equal(ln["out_op"], ops.to_operand(ln["out_f32"], prec)), "operand and fp32 outputs disagree"
-        ln["out_f32"].zero_(); ln["out_op"].zero_()
-
-
-def test_fused_layernorm_into_a_shared_border_map():
-    """ln_pad_gh / ln_pad_gw: the final LayerNorm writes the interior of the (gh + 1) x (gw + 1) map per image that the
-    head's tap GEMMs read; border rows stay untouched."""
-    ops = _ops()
-    prec, gh, gw, imgs, n, k = _lib.PREC_FP16X3, 16, 12, 5, 384, 1536
-    m = imgs * gh * gw
-    g = torch.Generator(device="cuda").manual_seed(7)
-    a, w = torch.randn(m, k, device="cuda", generator=g), torch.randn(n, k, device="cuda", generator=g) * 0.05
-    gamma, beta = torch.rand(n, device="cuda", generator=g) + 0.5, torch.randn(n, device="cuda", generator=g)
-    ln = dict(gamma=gamma, beta=beta, eps=1e-6, pad=(gh, gw))
-    ops.gemm(ops.to_operand(a, prec), ops.to_operand(w, prec), m, n, k, prec, ln=ln)
-    rows_p = imgs * (gh + 1) * (gw + 1)
-    got = ops.from_operand(ln["out_op"], rows_p, n, prec).view(imgs, gh + 1, gw + 1, n)
-    assert torch.equal(got[:, 1:, :gw].reshape(m, n), ops.from_operand(ops.to_operand(ln["out_f32"], prec), m, n, prec))
-    assert float(got[:, 0].abs().max()) == 0 and float(got[:, :, gw].abs().max()) == 0
