@@ -229,9 +229,9 @@ def test_operand_range_guard(setup):
 def test_l2_residency_of_the_residual_stream_changes_no_bit(setup, monkeypatch):
     """The encoder's launches carry an access-policy window that keeps the fp32 residual stream persisting in L2
     (common.cuh L2Window; PP_NO_L2_PERSIST=1, read when an engine is created, turns it off): a cache policy, so the
-    records must be identical, at a batch whose residual stream fits the carve-out and at one where only part does."""
+    records must be identical - for an engine that uses the carve-out and for one too large for it."""
     from probpose_code_b200.engine import Engine
-    for batch in (4, 48):
+    for batch in (4, 80):
         crops = synth.make_crops(batch, seed=90 + batch).cuda()
         on = Engine(precision="fp16x3", max_batch=batch).load_state_dict(setup["sd"])
         monkeypatch.setenv("PP_NO_L2_PERSIST", "1")
