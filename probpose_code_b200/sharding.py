@@ -72,6 +72,7 @@ class RecordGatherer:
         self.t0 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.t1 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         self.pending = [False, False]
+        self._timed = [True, True]
         self.comm = nccl_comm_ptr(self.device, group)
         self._ms, self._n = 0.0, 0
 
@@ -86,9 +87,7 @@ class RecordGatherer:
         valid after :meth:`wait` (or after the side stream reaches this point)."""
         from ._lib import check, lib
         j = i & 1
-        if self.pending[j] and self.t1[j].query():
-            self._ms += self.t0[j].elapsed_time(self.t1[j])
-            self._n += 1
+        self._harvest(j)
         self.decoded[j].record(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.decoded[j])
@@ -97,7 +96,16 @@ class RecordGatherer:
                                      self.stream.cuda_stream), "pp_allgather")
             self.t1[j].record(self.stream)
         self.pending[j] = True
+        self._timed[j] = False
         return self.recv[j]
+
+    def _harvest(self, j: int) -> None:
+        """Adds slot j's last gather to the statistics if it has completed (never waits: the host usually runs several
+        steps ahead of the device, so most gathers are only counted by :meth:`gather_ms`' final look)."""
+        if self.pending[j] and not self._timed[j] and self.t1[j].query():
+            self._ms += self.t0[j].elapsed_time(self.t1[j])
+            self._n += 1
+            self._timed[j] = True
 
     def wait(self) -> None:
         """The current stream waits for every outstanding gather."""
@@ -111,5 +119,9 @@ class RecordGatherer:
         self._ms, self._n = 0.0, 0
 
     def gather_ms(self) -> Optional[float]:
-        """Mean device time of a gather (side-stream events), over the gathers whose buffers have been reused."""
+        """Mean device time of a gather (side-stream events) over the gathers that had completed when their slot was
+        next looked at, plus - after waiting for the side stream - the outstanding ones."""
+        self.stream.synchronize()
+        for j in range(2):
+            self._harvest(j)
         return self._ms / self._n if self._n else None
