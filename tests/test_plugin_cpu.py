@@ -127,3 +127,41 @@ def test_pack_records_and_image_space_mapping():
     # topdown.py:165-167: kpts / input_size * input_scale + input_center - 0.5 * input_scale
     np.testing.assert_allclose(out[1].pred_instances.keypoints[0, 0], [192 / 192 * 96 + 500 - 48, 256 / 256 * 128 + 400 - 64])
     assert out[1].pred_instances.bboxes.shape == (1, 4)
+
+
+def test_two_phase_record_packing_matches_the_reference_arithmetic():
+    """The fused path builds the per-person containers before the records arrive (alloc_records) and fills the batch
+    arrays in place afterwards (fill_records): the values must be those of the reference's per-person arithmetic -
+    probmap.py:218 (`keypoints / [W - 1, H - 1] * input_size`, float64 through numpy's promotion) and
+    topdown.py:165-167 (`keypoints / input_size * input_scale + input_center - 0.5 * input_scale`) - bit for bit."""
+    from probpose_code_b200.mmpose_api.head import _record_xy
+    model = api.MODELS.build(api.probpose_small_cfg())
+    rng = np.random.default_rng(3)
+    b = 5
+    rec = rng.random((b, 17, 7), dtype=np.float32) * np.float32(47.0)
+    assert np.array_equal(_record_xy(rec), rec[:, :, :2])
+    codec = model.head.decoder
+    want_in = rec[:, :, :2] / [47, 63] * codec.input_size
+    assert np.array_equal(codec.keypoints_from_locs(rec[:, :, :2]), want_in)
+    assert np.array_equal(codec.keypoints_from_locs(rec[0, :, :2]), want_in[0])
+    samples = api.make_data_samples(b)
+    for i, s in enumerate(samples):
+        s.set_metainfo(dict(input_center=np.array([100.0 + 7 * i, 50.0 + i], dtype=np.float32),
+                            input_scale=np.array([90.0 + i, 120.0 + 3 * i], dtype=np.float32)))
+    arrays, preds = model.head.alloc_records(b)
+    geo = [(s.metainfo["input_size"], s.metainfo["input_scale"], s.metainfo["input_center"]) for s in samples]
+
+    def to_image(k):
+        out = np.empty_like(k)
+        for i, (size, scale, center) in enumerate(geo):
+            out[i] = k[i] / size * scale + center - 0.5 * scale
+        return out
+
+    model.head.fill_records(arrays, rec, to_image=to_image)
+    for i, p in enumerate(preds):
+        size, scale, center = geo[i]
+        assert np.array_equal(p.keypoints[0], want_in[i] / size * scale + center - 0.5 * scale)
+        assert p.keypoints.dtype == np.float64 and p.keypoints.shape == (1, 17, 2)
+        for j, name in enumerate(("keypoints_conf", "keypoints_probs", "keypoints_visible", "keypoints_oks", "keypoints_error")):
+            assert np.array_equal(getattr(p, name), rec[i:i + 1, :, 2 + j]) and getattr(p, name).dtype == np.float32
+        assert np.array_equal(p.keypoint_scores, rec[i:i + 1, :, 5])  # := oks (probmap_head.py:796-798)
