@@ -8,7 +8,6 @@ combination falls back to the reference's generic module-by-module flow (still C
 there is no CPU path)."""
 from __future__ import annotations
 
-from itertools import zip_longest
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -270,39 +269,38 @@ class TopdownPoseEstimator(nn.Module):
 
     def add_pred_to_datasample(self, batch_pred_instances: list, batch_pred_fields: Optional[list],
                                batch_data_samples: list, mapped: bool = False) -> list:
-        """topdown.py:128-194: input space -> image space, copy the bbox fields.  ``mapped``: the keypoints are
-        already in image space (the fused path maps the whole batch in one step)."""
-        assert len(batch_pred_instances) == len(batch_data_samples)
-        if batch_pred_fields is None:
-            batch_pred_fields = []
-        output_keypoint_indices = self.test_cfg.get("output_keypoint_indices", None)
-        for pred_instances, pred_fields, data_sample in zip_longest(batch_pred_instances, batch_pred_fields,
-                                                                    batch_data_samples):
-            if pred_instances is None:
+        """Attach the predictions to the data samples with the field semantics of topdown.py:128-194 (the evaluator
+        and the visualiser read these names): keypoints go from input space to image space
+        (``k / input_size * input_scale + input_center - 0.5 * input_scale``), ``keypoints_visible`` defaults to the
+        scores, ``output_keypoint_indices`` selects keypoints in every ``keypoint*`` field and in the per-keypoint
+        prediction fields, the ground-truth boxes are carried over.  ``mapped``: the keypoints are already in image
+        space (the fused path maps the whole batch in one vectorised step)."""
+        if len(batch_pred_instances) != len(batch_data_samples):
+            raise AssertionError("one prediction per data sample")
+        keep = self.test_cfg.get("output_keypoint_indices", None)
+        fields = list(batch_pred_fields) if batch_pred_fields else []
+        fields += [None] * (len(batch_data_samples) - len(fields))
+        for sample, inst, fld in zip(batch_data_samples, batch_pred_instances, fields):
+            if inst is None:
                 continue
-            gt_instances = data_sample.gt_instances
             if not mapped:
-                input_center = data_sample.metainfo["input_center"]
-                input_scale = data_sample.metainfo["input_scale"]
-                input_size = data_sample.metainfo["input_size"]
-            if not mapped:
-                pred_instances.keypoints[..., :2] = (pred_instances.keypoints[..., :2] / input_size * input_scale
-                                                     + input_center - 0.5 * input_scale)
-            if "keypoints_visible" not in pred_instances:
-                pred_instances.keypoints_visible = pred_instances.keypoint_scores
-            if output_keypoint_indices is not None:
-                num_keypoints = pred_instances.keypoints.shape[1]
-                for key, value in pred_instances.all_items():
-                    if key.startswith("keypoint"):
-                        pred_instances.set_field(value[:, output_keypoint_indices], key)
-            pred_instances.bboxes = gt_instances.bboxes
-            pred_instances.bbox_scores = gt_instances.bbox_scores
-            data_sample.pred_instances = pred_instances
-            if pred_fields is not None:
-                if output_keypoint_indices is not None:
-                    for key, value in pred_fields.all_items():
-                        if value.shape[0] != num_keypoints:
-                            continue
-                        pred_fields.set_field(value[output_keypoint_indices], key)
-                data_sample.pred_fields = pred_fields
+                meta = sample.metainfo
+                size, scale, center = meta["input_size"], meta["input_scale"], meta["input_center"]
+                inst.keypoints[..., :2] = inst.keypoints[..., :2] / size * scale + center - 0.5 * scale
+            if "keypoints_visible" not in inst:
+                inst.keypoints_visible = inst.keypoint_scores
+            if keep is not None:
+                n_kpt = inst.keypoints.shape[1]
+                for name, value in inst.all_items():
+                    if name.startswith("keypoint"):
+                        inst.set_field(value[:, keep], name)
+            gt = sample.gt_instances
+            inst.bboxes, inst.bbox_scores = gt.bboxes, gt.bbox_scores
+            sample.pred_instances = inst
+            if fld is not None:
+                if keep is not None:
+                    for name, value in fld.all_items():
+                        if value.shape[0] == n_kpt:
+                            fld.set_field(value[keep], name)
+                sample.pred_fields = fld
         return batch_data_samples

@@ -2,8 +2,8 @@
 the per-person CPU pipeline (GetBBoxCenterScale -> TopdownAffine -> PackPoseInputs -> pseudo_collate ->
 H2D) replaced by ONE frame upload and one GPU warp launch (``pp_crop_warp``), then ``pp_engine_infer``.
 
-Host-side geometry mirrors the reference line by line so that centres, scales and matrices are the
-same float32 values:
+Host-side geometry is computed for all boxes of a frame at once, with the reference's float32 operations per element,
+so that centres, scales and matrices are the same float32 values as those of:
   * ``bbox_xyxy2cs``            mmpose/structures/bbox/transforms.py:44-72
   * ``GetBBoxCenterScale``      mmpose/datasets/transforms/common_transforms.py:62-94
   * ``TopdownAffine``           mmpose/datasets/transforms/topdown_transforms.py:70-150 (``use_udp=True``)
@@ -21,46 +21,53 @@ from .structures import InstanceData, PoseDataSample
 
 
 def bbox_xywh2xyxy(bbox_xywh: np.ndarray) -> np.ndarray:
-    """structures/bbox/transforms.py:26-41."""
-    bbox_xyxy = bbox_xywh.copy()
-    bbox_xyxy[:, 2] = bbox_xyxy[:, 2] + bbox_xyxy[:, 0]
-    bbox_xyxy[:, 3] = bbox_xyxy[:, 3] + bbox_xyxy[:, 1]
-    return bbox_xyxy
+    """(N, 4+) boxes ``x, y, w, h`` -> ``x0, y0, x1, y1`` (what structures/bbox/transforms.py:26-41 returns)."""
+    out = np.array(bbox_xywh, copy=True)
+    out[:, 2:4] += out[:, 0:2]
+    return out
 
 
 def bbox_xyxy2cs(bbox: np.ndarray, padding: float = 1.0) -> Tuple[np.ndarray, np.ndarray]:
-    dim = bbox.ndim
-    if dim == 1:
-        bbox = bbox[None, :]
-    scale = (bbox[..., 2:] - bbox[..., :2]) * padding
-    center = (bbox[..., 2:] + bbox[..., :2]) * 0.5
-    if dim == 1:
-        center = center[0]
-        scale = scale[0]
-    return center, scale
+    """Boxes (4,) or (N, 4) -> centre and padded extent, the values of structures/bbox/transforms.py:44-72
+    (``(x1 + x0) * 0.5`` and ``(x1 - x0) * padding`` in the boxes' dtype)."""
+    lo, hi = bbox[..., 0:2], bbox[..., 2:4]
+    return (hi + lo) * 0.5, (hi - lo) * padding
+
+
+def fix_aspect(scales: np.ndarray, aspect: float) -> np.ndarray:
+    """Grow (N, 2) extents to width / height = ``aspect`` (``TopdownAffine._fix_aspect_ratio``,
+    topdown_transforms.py:70-91): the wider-than-``aspect`` boxes keep their width, the others their height."""
+    w, h = scales[:, 0], scales[:, 1]
+    wide = w > h * aspect
+    return np.stack([np.where(wide, w, h * aspect), np.where(wide, w / aspect, h)], axis=1)
+
+
+def udp_warp_matrices(centers: np.ndarray, scales: np.ndarray, rot: float, output_size: Tuple[int, int]) -> np.ndarray:
+    """(N, 2) centres and extents -> the (N, 2, 3) float32 matrices ``TopdownAffine(use_udp=True)`` hands to
+    ``cv2.warpAffine``, for all persons of a frame in one pass.  Every entry is formed by the float32 operations, in the
+    order, of ``get_udp_warp_matrix`` (structures/bbox/transforms.py:315-359) - the crops are compared with the
+    reference's bit for bit, and a last-bit difference in a matrix moves pixels (tests/golden/crop_kat.npz)."""
+    ang = float(np.deg2rad(rot))
+    c, s = math.cos(ang), math.sin(ang)
+    gx, gy = (output_size[0] - 1) / scales[:, 0], (output_size[1] - 1) / scales[:, 1]  # python int / float32 column: float32
+    ex, ey = centers[:, 0] * 2, centers[:, 1] * 2                                    # "input_size = center * 2"
+    m = np.zeros((centers.shape[0], 2, 3), dtype=np.float32)
+    m[:, 0, 0], m[:, 0, 1] = c * gx, -s * gx
+    m[:, 1, 0], m[:, 1, 1] = s * gy, c * gy
+    m[:, 0, 2] = gx * (-0.5 * ex * c + 0.5 * ey * s + 0.5 * scales[:, 0])
+    m[:, 1, 2] = gy * (-0.5 * ex * s - 0.5 * ey * c + 0.5 * scales[:, 1])
+    return m
 
 
 def get_udp_warp_matrix(center: np.ndarray, scale: np.ndarray, rot: float, output_size: Tuple[int, int]) -> np.ndarray:
-    assert len(center) == 2
-    assert len(scale) == 2
-    assert len(output_size) == 2
-    input_size = center * 2
-    rot_rad = np.deg2rad(rot)
-    warp_mat = np.zeros((2, 3), dtype=np.float32)
-    scale_x = (output_size[0] - 1) / scale[0]
-    scale_y = (output_size[1] - 1) / scale[1]
-    warp_mat[0, 0] = math.cos(rot_rad) * scale_x
-    warp_mat[0, 1] = -math.sin(rot_rad) * scale_x
-    warp_mat[0, 2] = scale_x * (-0.5 * input_size[0] * math.cos(rot_rad) + 0.5 * input_size[1] * math.sin(rot_rad) + 0.5 * scale[0])
-    warp_mat[1, 0] = math.sin(rot_rad) * scale_y
-    warp_mat[1, 1] = math.cos(rot_rad) * scale_y
-    warp_mat[1, 2] = scale_y * (-0.5 * input_size[0] * math.sin(rot_rad) - 0.5 * input_size[1] * math.cos(rot_rad) + 0.5 * scale[1])
-    return warp_mat
+    """One person's matrix (the reference's signature); see :func:`udp_warp_matrices`."""
+    assert len(center) == 2 and len(scale) == 2 and len(output_size) == 2
+    return udp_warp_matrices(np.asarray(center)[None], np.asarray(scale)[None], rot, output_size)[0]
 
 
 class TopdownAffine:
-    """Geometry of ``TopdownAffine(input_size, use_udp=True, input_padding)``; the pixel work (cv2.warpAffine)
-    is done for all persons at once on the GPU by :func:`inference_topdown`."""
+    """Geometry of ``TopdownAffine(input_size, use_udp=True, input_padding)`` for all boxes of a frame at once; the pixel
+    work (cv2.warpAffine) is done for all persons by one GPU launch in :func:`inference_topdown`."""
 
     def __init__(self, input_size: Tuple[int, int], input_padding: float = 1.25, use_udp: bool = False) -> None:
         assert len(input_size) == 2 and all(isinstance(i, int) for i in input_size), f"Invalid input_size {input_size}"
@@ -70,19 +77,18 @@ class TopdownAffine:
         self.use_udp = use_udp
         self.input_padding = input_padding
 
-    @staticmethod
-    def _fix_aspect_ratio(bbox_scale: np.ndarray, aspect_ratio: float):
-        w, h = np.hsplit(bbox_scale, [1])
-        return np.where(w > h * aspect_ratio, np.hstack([w, w / aspect_ratio]), np.hstack([h * aspect_ratio, h]))
+    def batch_geometry(self, bboxes: np.ndarray):
+        """(N, 4) xyxy -> centres (N, 2), aspect-fixed extents (N, 2), matrices (N, 2, 3) float32
+        (GetBBoxCenterScale + topdown_transforms.py:93-118 for every box)."""
+        w, h = self.input_size
+        centers, scales = bbox_xyxy2cs(bboxes, padding=self.input_padding)
+        scales = fix_aspect(scales, w / h)
+        return centers, scales, udp_warp_matrices(centers, scales, 0.0, (w, h))
 
     def geometry(self, bbox: np.ndarray):
-        """bbox (1, 4) xyxy -> (center (2,), scale (2,), warp_mat (2, 3) float32), topdown_transforms.py:93-118."""
-        w, h = self.input_size
-        _c, _s = bbox_xyxy2cs(bbox, padding=self.input_padding)
-        bbox_center, bbox_scale = _c.reshape(1, 2), _s.reshape(1, 2)
-        bbox_scale = self._fix_aspect_ratio(bbox_scale, aspect_ratio=w / h)
-        center, scale = bbox_center[0], bbox_scale[0]
-        return center, scale, get_udp_warp_matrix(center, scale, 0.0, output_size=(w, h))
+        """One box, (1, 4) xyxy -> (center (2,), scale (2,), warp_mat (2, 3) float32)."""
+        c, s, m = self.batch_geometry(np.asarray(bbox).reshape(1, -1)[:, :4])
+        return c[0], s[0], m[0]
 
 
 def inference_topdown(model, img: Union[np.ndarray, torch.Tensor], bboxes: Optional[Union[List, np.ndarray]] = None,
@@ -113,16 +119,15 @@ def inference_topdown(model, img: Union[np.ndarray, torch.Tensor], bboxes: Optio
     in_w, in_h = int(codec.input_size[0]), int(codec.input_size[1])
     affine = TopdownAffine(input_size=(in_w, in_h), use_udp=True, input_padding=getattr(model, "input_padding", 1.25))
     fi = list(flip_indices if flip_indices is not None else COCO_FLIP_INDICES)
-    samples, mats = [], []
-    for bbox in bboxes:
-        bbox = np.asarray(bbox)[None, :4]  # shape (1, 4), inference.py:185
-        center, scale, m = affine.geometry(bbox)
+    boxes = np.asarray(bboxes)[:, :4]
+    centers, scales, mats = affine.batch_geometry(boxes)  # every person of the frame in one pass
+    samples = []
+    for i in range(boxes.shape[0]):
         # ori_shape / img_shape: what LoadImage + PackPoseInputs record (merge_data_samples reads ori_shape)
-        ds = PoseDataSample(metainfo=dict(input_size=(in_w, in_h), input_center=center, input_scale=scale, flip_indices=fi,
-                                          ori_shape=(h, w), img_shape=(h, w)))
-        ds.gt_instances = InstanceData(bboxes=bbox, bbox_scores=np.ones(1, dtype=np.float32))
+        ds = PoseDataSample(metainfo=dict(input_size=(in_w, in_h), input_center=centers[i], input_scale=scales[i],
+                                          flip_indices=fi, ori_shape=(h, w), img_shape=(h, w)))
+        ds.gt_instances = InstanceData(bboxes=boxes[i:i + 1], bbox_scores=np.ones(1, dtype=np.float32))
         samples.append(ds)
-        mats.append(m)
     dev = model._device()
     if isinstance(img, np.ndarray):
         if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
@@ -131,5 +136,5 @@ def inference_topdown(model, img: Union[np.ndarray, torch.Tensor], bboxes: Optio
     else:
         frame = img.to(dev).contiguous()
     with torch.no_grad():
-        crops = ops.crop_warp(frame, torch.from_numpy(np.stack(mats)).to(dev), out_hw=(in_h, in_w))
+        crops = ops.crop_warp(frame, torch.from_numpy(mats).to(dev), out_hw=(in_h, in_w))
         return model.test_step(dict(inputs=crops, data_samples=samples))

@@ -165,3 +165,28 @@ def test_two_phase_record_packing_matches_the_reference_arithmetic():
         for j, name in enumerate(("keypoints_conf", "keypoints_probs", "keypoints_visible", "keypoints_oks", "keypoints_error")):
             assert np.array_equal(getattr(p, name), rec[i:i + 1, :, 2 + j]) and getattr(p, name).dtype == np.float32
         assert np.array_equal(p.keypoint_scores, rec[i:i + 1, :, 5])  # := oks (probmap_head.py:796-798)
+
+
+def test_frame_geometry_matches_the_reference_functions_bit_for_bit():
+    """mmpose_api.inference computes centres, extents and UDP matrices for all boxes of a frame in one pass; they must be
+    the float32 values the genuine bbox_xyxy2cs / _fix_aspect_ratio / get_udp_warp_matrix produced per person
+    (tests/golden/crop_kat.npz, oracle/gen_golden_crops.py), singly and batched."""
+    import os
+    from probpose_code_b200.mmpose_api.inference import TopdownAffine, bbox_xywh2xyxy, get_udp_warp_matrix
+    kat = np.load(os.path.join(os.path.dirname(__file__), "golden", "crop_kat.npz"))
+    aff = TopdownAffine(input_size=(192, 256), use_udp=True, input_padding=1.25)
+    for fi in range(3):
+        boxes = kat[f"f{fi}/boxes"]
+        c, s, m = aff.batch_geometry(boxes)
+        assert m.dtype == np.float32
+        np.testing.assert_array_equal(c, kat[f"f{fi}/centers"])
+        np.testing.assert_array_equal(s, kat[f"f{fi}/scales"])
+        np.testing.assert_array_equal(m, kat[f"f{fi}/mats"])
+        c1, s1, m1 = aff.geometry(boxes[3][None])
+        np.testing.assert_array_equal(m1, kat[f"f{fi}/mats"][3])
+        np.testing.assert_array_equal(get_udp_warp_matrix(c1, s1, 0.0, (192, 256)), m1)
+    xywh = np.array([[10.0, 20.0, 30.0, 40.0, 0.9]], dtype=np.float32)
+    np.testing.assert_array_equal(bbox_xywh2xyxy(xywh), np.array([[10.0, 20.0, 40.0, 60.0, 0.9]], dtype=np.float32))
+    assert xywh[0, 2] == 30.0  # the input is not modified
+    rot = get_udp_warp_matrix(np.array([50.0, 60.0], np.float32), np.array([90.0, 120.0], np.float32), 30.0, (192, 256))
+    assert rot.shape == (2, 3) and abs(rot[0, 0] - np.cos(np.pi / 6) * 191 / 90) < 1e-5
