@@ -73,6 +73,7 @@ struct pp_engine {
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   int graph_max_images = 0;           // replay when passes * batch <= this; 0 = off, < 0 = no limit
   int64_t graph_replays = 0;
+  bool group_phases = true;  // the four phases of a deconvolution as one grouped GEMM launch (PP_NO_GROUPED_GEMM=1: four launches)
   size_t l2_setaside = 0;  // persisting-L2 carve-out available for the residual stream (0: off)
   size_t l2_max_window = 0;  // largest access-policy window of the device (informative)
   size_t g_stride = 0;  // bytes between the per-branch tap-gather buffers
@@ -301,6 +302,13 @@ static int gemm(pp_engine* e, const pp_gemm_args& g, cudaStream_t st) {
   return timed(e, PP_KC_GEMM, st, [&] { return gemm_dispatch(g, st); });
 }
 
+// `count` GEMMs that share everything but W, the tap shifts and the phase: one launch (gemm_dispatch_group).
+static int gemm_group(pp_engine* e, const pp_gemm_args* g, int count, cudaStream_t st) {
+  if (e->profiling)
+    for (int i = 0; i < count; ++i) e->prof_gemm_flops += 2.0 * g[i].m * g[i].n * g[i].k;
+  return timed(e, PP_KC_GEMM, st, [&] { return gemm_dispatch_group(g, count, st); });
+}
+
 #define PP_TRY(expr)            \
   do {                          \
     const int _rc = (expr);     \
@@ -389,9 +397,11 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
     const int64_t rows = (int64_t)n_img * (h + 1) * (w + 1);
     const void* src = i == 0 ? e->at<>(e->feat_op) : e->at<>(e->d1_op);
     void* dst = i == 0 ? e->at<>(e->d1_op) : e->at<>(e->d2_op);
+    pp_gemm_args phases[4];  // the four sub-pixel phases: one grouped launch
     for (int ph = 0; ph < 4; ++ph) {
       const int py = ph >> 1, px = ph & 1;
-      pp_gemm_args g = gemm_args(e, rows, DC, 4 * cin, src, e->at<>(e->w_dc[i][ph]));
+      pp_gemm_args& g = phases[ph];
+      g = gemm_args(e, rows, DC, 4 * cin, src, e->at<>(e->w_dc[i][ph]));
       g.a_taps = 4;
       for (int t = 0; t < 4; ++t) {
         int dy, dx, kk;
@@ -404,7 +414,11 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
       g.in_pad = 2; g.in_h = h; g.in_w = w; g.out_pad = i == 0 ? 2 : 0;
       g.up_hin = h; g.up_win = w; g.up_py = py; g.up_px = px;
       if (e->profiling) e->prof_gemm_flops -= 2.0 * (rows - (double)n_img * h * w) * DC * 4 * cin;  // border rows are not algorithmic work
-      PP_TRY(gemm(e, g, st));
+    }
+    if (e->group_phases) {
+      PP_TRY(gemm_group(e, phases, 4, st));
+    } else {
+      for (int ph = 0; ph < 4; ++ph) PP_TRY(gemm(e, phases[ph], st));
     }
   }
   {
@@ -593,6 +607,7 @@ extern "C" int pp_engine_create(const pp_engine_cfg* cfg, void* workspace, size_
     }
     cudaGetLastError();  // an unsupported limit is not an error of the engine
   }
+  e->group_phases = getenv("PP_NO_GROUPED_GEMM") == nullptr;
   {  // graph replay of small calls is on by default; PP_ENGINE_GRAPH = 0 (off), -1 (every size) or a limit in images
     const char* env = getenv("PP_ENGINE_GRAPH");
     e->graph_max_images = env ? atoi(env) : kGraphDefaultMaxImages;

@@ -76,6 +76,8 @@ int launch_fold_bn(const float* gamma, const float* beta, const float* mean, con
 
 // pp_gemm without the C-ABI argument checks (gemm.cu).
 int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st);
+// `count` (<= 4) GEMMs that differ only in W, a_tap_shift and (up_py, up_px) as one launch (gemm_tc.cu "Grouped launch").
+int gemm_dispatch_group(const pp_gemm_args* a, int count, cudaStream_t st);
 
 inline void deconv_tap(int phase, int tap, int* d, int* k) {  // see launch_pack_deconv_phase
   if (phase == 0) { *d = tap == 0 ? 0 : -1; *k = tap == 0 ? 1 : 3; }

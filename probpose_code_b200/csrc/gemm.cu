@@ -5,6 +5,7 @@
 namespace pp {
 
 int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaStream_t st);  // gemm_tc.cu
+int gemm_tc_launch_group(const pp_gemm_args* a, const EpiParams& e0, int count, cudaStream_t st);
 
 // ---- fp32 FFMA GEMM (PP_PREC_FP32_SIMT): 64x64 tile, 256 threads, 4x4 outputs each ----------
 // Exists to verify the tensor-core path on the GPU itself (same epilogue, same layouts).
@@ -89,8 +90,7 @@ extern "C" int pp_operand_from_f32(int32_t precision, const float* src, int64_t 
 
 namespace pp {
 
-int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st) {
-  if (a.m == 0) return PP_OK;
+static EpiParams make_epi(const pp_gemm_args& a) {
   EpiParams e;
   e.scale = a.scale; e.shift = a.shift; e.residual = a.residual; e.d = a.d;
   e.m = a.m; e.n = a.n; e.act = a.act; e.out_kind = a.out_kind; e.ldd = a.ldd; e.plane = a.plane;
@@ -99,6 +99,28 @@ int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st) {
   e.in_h = a.in_pad ? a.in_h : a.up_hin; e.in_w = a.in_pad ? a.in_w : a.up_win;
   if (a.out_pad && !a.in_pad && !a.up_hin) { e.in_h = a.in_h; e.in_w = a.in_w; }
   e.res_mod = a.res_mod;
+  return e;
+}
+
+int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st);
+
+// `count` GEMMs that share everything but W, the tap shifts and the ConvTranspose2d phase: one persistent launch on the
+// tensor-core path (gemm_tc.cu "Grouped launch"), one launch each on the CUDA-core verification path.
+int gemm_dispatch_group(const pp_gemm_args* a, int count, cudaStream_t st) {
+  if (count <= 0 || a[0].m == 0) return PP_OK;
+  if (a[0].precision == PP_PREC_FP32_SIMT || count == 1) {
+    for (int g = 0; g < count; ++g) {
+      const int rc = gemm_dispatch(a[g], st);
+      if (rc != PP_OK) return rc;
+    }
+    return PP_OK;
+  }
+  return gemm_tc_launch_group(a, make_epi(a[0]), count, st);
+}
+
+int gemm_dispatch(const pp_gemm_args& a, cudaStream_t st) {
+  if (a.m == 0) return PP_OK;
+  const EpiParams e = make_epi(a);
   if (a.precision == PP_PREC_FP32_SIMT) {
     SimtTaps tp = {};
     tp.taps = a.a_taps > 1 ? a.a_taps : 1;

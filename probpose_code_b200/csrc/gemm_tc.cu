@@ -52,6 +52,19 @@ struct TapParams {
   int shift[kMaxTaps];
 };
 
+// Grouped launch: up to kMaxGroups GEMMs that share A, the output buffer, the shapes and the epilogue - the four
+// sub-pixel phases of a ConvTranspose2d(k4, s2, p1) - run as ONE persistent launch.  Group 0 is described by the plain
+// arguments; groups 1.. bring their own W operand, tap shifts and phase.  Tiles are ordered (m, group, n), so the phases of
+// a row block run side by side (one pass over the A rows in L2), the launch has one fill / drain instead of four and the
+// last round of the tile walk is shared (deconv-2 at batch 64: 4 x 826 tiles on 74 CTA pairs, 45 rounds instead of 4 x 12).
+constexpr int kMaxGroups = 4;
+struct GroupParams {
+  CUtensorMap tm_w[kMaxGroups - 1];
+  int groups;  // 1 = plain launch
+  int shift[kMaxGroups - 1][kMaxTaps];
+  int up_py[kMaxGroups - 1], up_px[kMaxGroups - 1];
+};
+
 // ACCS (FP16X3 only): 1 = all three products accumulate into one TMEM accumulator (wide tiles keep
 // both TMEM stages); 2 = the cross terms hi.lo + lo.hi go to a second accumulator, so the big
 // accumulator is rounded once per k-slice instead of three times (used for long K, see pick_config).
@@ -195,7 +208,8 @@ __device__ __forceinline__ void store_operand4_row(void* base, int64_t rowk, int
 template <int BN, int SPLIT, bool BF16, int OUT, int ACCS, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const int K,
-               const int num_m_tiles, const int num_n_tiles, const TapParams tp, const EpiParams e) {
+               const int num_m_tiles, const int num_n_tiles, const TapParams tp, const EpiParams e,
+               const __grid_constant__ GroupParams gp) {
   using Cfg = GemmCfg<BN, SPLIT, ACCS, PAIR>;
   static_assert(ACCS == 1 || SPLIT == 3, "a second accumulator only exists in the split mode");
   constexpr int PREC = SPLIT == 3 ? PP_PREC_FP16X3 : (BF16 ? PP_PREC_BF16 : PP_PREC_FP16);
@@ -218,7 +232,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = K / BK;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int G = gp.groups;
+  const int gn_tiles = G * num_n_tiles;  // tiles per row block: (group, n)
+  const int num_tiles = num_m_tiles * gn_tiles;
   // work-unit walk: a CTA (or a CTA pair) starts at its index and strides by the number of units
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -262,30 +278,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int a_lo = tp.tap_k;  // column of the lo plane inside an FP16X3 A row
       uint32_t it = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
-        const int m0 = (tile / num_n_tiles) * TILE_M + (int)cta_rank * kBM;
+        const int m0 = (tile / gn_tiles) * TILE_M + (int)cta_rank * kBM;
+        const int gi = (tile % gn_tiles) / num_n_tiles;  // group: its own W operand and tap shifts
         const int n0 = (tile % num_n_tiles) * BN + (int)cta_rank * Cfg::BN_CTA;  // pair: this CTA's half of the W tile
+        const CUtensorMap* tmw = gi == 0 ? &tm_w : &gp.tm_w[gi - 1];
+        const int* shifts = gi == 0 ? tp.shift : gp.shift[gi - 1];
         int tap = 0, kc = 0;  // current tap and its k-block
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          const int arow = m0 + tp.shift[tap];
+          const int arow = m0 + shifts[tap];
           if constexpr (PAIR) {
             // both CTAs' bytes are credited to the leader's barrier; only the leader arms it
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
             ptx::tma_load_2d_2cta(stage_a(s, 0), &tm_a, &full_bar[s], kc * BK, arow);
-            ptx::tma_load_2d_2cta(stage_b(s, 0), &tm_w, &full_bar[s], kb * BK, n0);
+            ptx::tma_load_2d_2cta(stage_b(s, 0), tmw, &full_bar[s], kb * BK, n0);
             if constexpr (SPLIT == 3) {
               ptx::tma_load_2d_2cta(stage_a(s, 1), &tm_a, &full_bar[s], a_lo + kc * BK, arow);
-              ptx::tma_load_2d_2cta(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * BK, n0);
+              ptx::tma_load_2d_2cta(stage_b(s, 1), tmw, &full_bar[s], K + kb * BK, n0);
             }
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             ptx::tma_load_2d(stage_a(s, 0), &tm_a, &full_bar[s], kc * BK, arow);
-            ptx::tma_load_2d(stage_b(s, 0), &tm_w, &full_bar[s], kb * BK, n0);
+            ptx::tma_load_2d(stage_b(s, 0), tmw, &full_bar[s], kb * BK, n0);
             if constexpr (SPLIT == 3) {
               ptx::tma_load_2d(stage_a(s, 1), &tm_a, &full_bar[s], a_lo + kc * BK, arow);
-              ptx::tma_load_2d(stage_b(s, 1), &tm_w, &full_bar[s], K + kb * BK, n0);
+              ptx::tma_load_2d(stage_b(s, 1), tmw, &full_bar[s], K + kb * BK, n0);
             }
           }
           if (++kc == kb_per_tap) { kc = 0; ++tap; }
@@ -352,7 +371,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr float acc_scale = SPLIT == 3 ? kAccScaleInv : 1.0f;  // FP16X3 operands carry 64 x 64
     uint32_t lt = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++lt) {
-      const int m0 = (tile / num_n_tiles) * TILE_M + (int)cta_rank * kBM, n0 = (tile % num_n_tiles) * BN;
+      const int m0 = (tile / gn_tiles) * TILE_M + (int)cta_rank * kBM, n0 = (tile % num_n_tiles) * BN;
+      const int gi = (tile % gn_tiles) / num_n_tiles;
+      const int up_py = gi == 0 ? e.up_py : gp.up_py[gi - 1], up_px = gi == 0 ? e.up_px : gp.up_px[gi - 1];
       const int as = lt % ACC_STAGES;
       const uint32_t aph = (lt / ACC_STAGES) & 1;
       const int row_base = m0 + q * 32;
@@ -382,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           for (int i = 0; i < 8; ++i) {
             const bool ok = (m_first + 4 * i < e.m) && pj >= ig.xo && pj < e.in_w + ig.xo && pi >= ig.yo && pi < e.in_h + ig.yo;
             const int ii = pi - ig.yo, jj = pj - ig.xo;
-            const int oy = e.up_hin ? 2 * ii + e.up_py + og.yo : ii + og.yo, ox = e.up_hin ? 2 * jj + e.up_px + og.xo : jj + og.xo;
+            const int oy = e.up_hin ? 2 * ii + up_py + og.yo : ii + og.yo, ox = e.up_hin ? 2 * jj + up_px + og.xo : jj + og.xo;
             const int64_t orow = (int64_t)(pb * oh + oy) * ow + ox;
             doff[i] = ok ? orow * e.ldd : -1;
             roff[i] = orow * e.ldd;
@@ -513,7 +534,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + rsub;
               bool ok;
-              const int64_t orow = map_out_row(e, row_base + r, ok);
+              EpiParams eg = e;  // this group's phase
+              eg.up_py = up_py; eg.up_px = up_px;
+              const int64_t orow = map_out_row(eg, row_base + r, ok);
               if (!ok) continue;
               const int64_t rrow = e.res_mod > 0 ? (int)orow % e.res_mod : orow;
               const uint32_t src = stg + r * 128 + ((c4 ^ (r & 7)) << 4);
@@ -606,6 +629,16 @@ int make_operand_map(CUtensorMap* out, const void* base, int64_t rows, int64_t r
 
 static int num_sms() { return device_sm_count(); }
 
+// The group of the launch being dispatched (gemm_tc_launch_group sets it around gemm_tc_launch): the W operands, tap
+// shifts and phases of groups 1.. (group 0 travels in the plain arguments).
+struct GroupHost {
+  int groups;
+  const void* w[kMaxGroups - 1];
+  int shift[kMaxGroups - 1][kMaxTaps];
+  int up_py[kMaxGroups - 1], up_px[kMaxGroups - 1];
+};
+static thread_local const GroupHost* g_group = nullptr;
+
 template <int BN, int SPLIT, bool BF16, int OUT, int ACCS, bool PAIR>
 static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams& tp, cudaStream_t st) {
   using Cfg = GemmCfg<BN, SPLIT, ACCS, PAIR>;
@@ -618,9 +651,21 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams&
   if (rc) return rc;
   rc = make_operand_map(&tmw, a.w, a.n, (int64_t)nops * a.k, Cfg::BN_CTA, Cfg::BK, BF16);
   if (rc) return rc;
+  GroupParams gp = {};
+  gp.groups = 1;
+  if (g_group != nullptr) {
+    gp.groups = g_group->groups;
+    for (int g = 1; g < gp.groups; ++g) {
+      rc = make_operand_map(&gp.tm_w[g - 1], g_group->w[g - 1], a.n, (int64_t)nops * a.k, Cfg::BN_CTA, Cfg::BK, BF16);
+      if (rc) return rc;
+      for (int t = 0; t < kMaxTaps; ++t) gp.shift[g - 1][t] = g_group->shift[g - 1][t];
+      gp.up_py[g - 1] = g_group->up_py[g - 1];
+      gp.up_px[g - 1] = g_group->up_px[g - 1];
+    }
+  }
   constexpr int TILE_M = PAIR ? 2 * kBM : kBM;
   const int mt = (a.m + TILE_M - 1) / TILE_M, nt = (a.n + BN - 1) / BN;
-  const int64_t tiles = (int64_t)mt * nt;
+  const int64_t tiles = (int64_t)mt * nt * gp.groups;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -644,7 +689,7 @@ static int launch_tc(const pp_gemm_args& a, const EpiParams& e, const TapParams&
   cfg.attrs = attr;
   cfg.numAttrs = na;
   const int k = a.k;
-  PP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tma, tmw, k, mt, nt, tp, e));
+  PP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tma, tmw, k, mt, nt, tp, e, gp));
   count_launch();
   return PP_OK;
 }
@@ -739,6 +784,30 @@ int gemm_tc_launch(const pp_gemm_args& a, const EpiParams& e, int tile_n, cudaSt
   }
   set_error("pp_gemm: precision %d is not a tensor-core mode", a.precision);
   return PP_ERR_INVALID;
+}
+
+// `count` GEMMs that differ only in their W operand, tap shifts and ConvTranspose2d phase (up_py, up_px), as one launch.
+int gemm_tc_launch_group(const pp_gemm_args* a, const EpiParams& e0, int count, cudaStream_t st) {
+  PP_REQUIRE(count >= 1 && count <= kMaxGroups, PP_ERR_INVALID, "grouped GEMM: %d groups outside [1, %d]", count, kMaxGroups);
+  GroupHost gh = {};
+  gh.groups = count;
+  for (int g = 1; g < count; ++g) {
+    const pp_gemm_args& b = a[g];
+    PP_REQUIRE(b.precision == a[0].precision && b.m == a[0].m && b.n == a[0].n && b.k == a[0].k && b.a == a[0].a && b.d == a[0].d &&
+                   b.scale == a[0].scale && b.shift == a[0].shift && b.residual == a[0].residual && b.act == a[0].act &&
+                   b.out_kind == a[0].out_kind && b.ldd == a[0].ldd && b.a_taps == a[0].a_taps && b.in_pad == a[0].in_pad &&
+                   b.out_pad == a[0].out_pad && b.in_h == a[0].in_h && b.in_w == a[0].in_w && b.up_hin == a[0].up_hin &&
+                   b.up_win == a[0].up_win && b.tile_n == a[0].tile_n && b.cta_pair == a[0].cta_pair,
+               PP_ERR_INVALID, "grouped GEMM: group %d differs from group 0 in more than W, tap shifts and phase", g);
+    gh.w[g - 1] = b.w;
+    for (int t = 0; t < kMaxTaps; ++t) gh.shift[g - 1][t] = b.a_taps > 1 ? b.a_tap_shift[t] : 0;
+    gh.up_py[g - 1] = b.up_py;
+    gh.up_px[g - 1] = b.up_px;
+  }
+  g_group = &gh;
+  const int rc = gemm_tc_launch(a[0], e0, a[0].tile_n, st);
+  g_group = nullptr;
+  return rc;
 }
 
 }  // namespace pp

@@ -239,3 +239,29 @@ def test_l2_residency_of_the_residual_stream_changes_no_bit(setup, monkeypatch):
         monkeypatch.delenv("PP_NO_L2_PERSIST")
         for flip in (True, False):
             assert torch.equal(on.infer(crops, flip_test=flip), off.infer(crops, flip_test=flip))
+
+
+@pytest.mark.parametrize("head_kind", ["probmap", "heatmap"])
+def test_grouped_deconvolution_phases_change_no_bit(setup, monkeypatch, head_kind):
+    """The four sub-pixel phases of each deconvolution run as ONE grouped tcgen05 GEMM launch (gemm_tc.cu "Grouped
+    launch"; PP_NO_GROUPED_GEMM=1, read when an engine is created, launches them one by one).  Same tiles, same
+    arithmetic: logits and records must be identical, and the grouped engine launches six kernels fewer."""
+    from probpose_code_b200.engine import Engine
+    sd = setup["sd"] if head_kind == "probmap" else {k: v for k, v in synth.make_state_dict(seed=0).items()
+                                                      if k.startswith("backbone.") or k.startswith("head.deconv") or k.startswith("head.final")}
+    kw = dict(precision="fp16x3", max_batch=6, head_kind=head_kind)
+    grouped = Engine(**kw).load_state_dict(sd)
+    monkeypatch.setenv("PP_NO_GROUPED_GEMM", "1")
+    single = Engine(**kw).load_state_dict(sd)
+    monkeypatch.delenv("PP_NO_GROUPED_GEMM")
+    for e in (grouped, single):
+        e.set_graph(0)
+    crops = synth.make_crops(5, seed=123).cuda()
+    for flip in (True, False):
+        a, b = grouped.infer(crops, flip_test=flip), single.infer(crops, flip_test=flip)
+        assert torch.equal(a, b)
+        assert single.last_launch_count - grouped.last_launch_count == 6
+    if head_kind == "probmap":
+        la, sa = grouped.head(setup["feat"].cuda().contiguous())
+        lb, sb = single.head(setup["feat"].cuda().contiguous())
+        assert torch.equal(la, lb) and torch.equal(sa, sb)
