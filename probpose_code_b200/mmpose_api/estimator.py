@@ -246,6 +246,8 @@ class TopdownPoseEstimator(nn.Module):
         # The device is busy for milliseconds: build everything that does not need the results now - the per-person
         # containers (views of fresh batch arrays), the bbox fields, the geometry of topdown.py:165-167 - and only
         # then wait for the records and fill the batch arrays in place.
+        if records.shape[0] == 0:
+            return data_samples
         arrays, preds = self.head.alloc_records(records.shape[0])
         self.add_pred_to_datasample(preds, fields, data_samples, mapped=True)
         geo = np.concatenate([a for d in data_samples for m in (d.metainfo,)
