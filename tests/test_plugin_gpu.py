@@ -102,3 +102,45 @@ def test_output_heatmaps_and_weight_refresh(world):
     assert (after > before).all()
     with torch.no_grad():
         m.head.probability_layers[12].bias.sub_(1.0)
+
+
+@pytest.mark.parametrize("n", [1, 3, 5, 9])
+def test_every_input_form_gives_the_same_samples(world, n):
+    """test_step accepts what mmengine's pseudo_collate hands over (a list of pageable per-person tensors: gathered in
+    quarters into pinned memory), a stacked pageable tensor, a pinned tensor and a device tensor; whatever the form and the
+    batch size (quarters of unequal length, a single person), the samples must be the same bit for bit - keypoints in
+    image space for per-person boxes, all seven fields, containers that are views of one batch array each - and a
+    second call must not change what the first one returned."""
+    m = world["model"]
+    m.test_cfg["flip_test"] = True
+    crops = synth.make_crops(n, seed=60 + n)
+
+    def samples():
+        s = api.make_data_samples(n)
+        for i, d_ in enumerate(s):
+            d_.set_metainfo(dict(input_center=np.array([300.0 + 11 * i, 200.0 - 3 * i], dtype=np.float32),
+                                 input_scale=np.array([150.0 + i, 200.0 + 2 * i], dtype=np.float32)))
+        return s
+
+    forms = dict(list=[c.clone() for c in crops], stacked=crops.clone(), pinned=crops.clone().pin_memory(), device=crops.cuda())
+    outs = {k: m.test_step(dict(inputs=v, data_samples=samples())) for k, v in forms.items()}
+    names = ("keypoints", "keypoint_scores", "keypoints_conf", "keypoints_probs", "keypoints_visible", "keypoints_oks", "keypoints_error")
+    first = {k: {f: np.array(getattr(o.pred_instances, f)) for f in names} for k, o in zip(range(n), outs["list"])}
+    for form, out in outs.items():
+        assert len(out) == n
+        for i, o in enumerate(out):
+            for f in names:
+                assert np.array_equal(getattr(o.pred_instances, f), first[i][f]), f"{form}: person {i} field {f}"
+            assert o.pred_instances.keypoints.shape == (1, 17, 2) and o.pred_instances.keypoints.dtype == np.float64
+            assert np.array_equal(o.pred_instances.bboxes, o.gt_instances.bboxes)
+    # image-space mapping (topdown.py:165-167) against the same crop run alone with the identity geometry of
+    # make_data_samples (bbox = whole image: image space == input space up to the last bit)
+    k_in = m.test_step(dict(inputs=crops[:1], data_samples=api.make_data_samples(1)))[0].pred_instances.keypoints
+    meta = outs["list"][0].metainfo
+    want = k_in / meta["input_size"] * meta["input_scale"] + meta["input_center"] - 0.5 * meta["input_scale"]
+    assert np.abs(outs["list"][0].pred_instances.keypoints - want).max() <= 1e-9
+    # results of an earlier call are not views of a reused staging buffer
+    m.test_step(dict(inputs=synth.make_crops(n, seed=999), data_samples=samples()))
+    for i, o in enumerate(outs["list"]):
+        for f in names:
+            assert np.array_equal(getattr(o.pred_instances, f), first[i][f])
