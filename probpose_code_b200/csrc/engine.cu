@@ -460,6 +460,10 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
       pp_gemm_args g = gemm_args(e, rows, D, 9 * D, gbuf, e->at<>(j == 1 ? e->w_c2[br] : e->w_c3[br]));
       g.scale = e->at<float>(e->c_scale[j]) + br * D; g.shift = e->at<float>(e->c_shift[j]) + br * D;
       g.ldd = 4 * D; g.d = e->at<float>(e->c_f32) + br * D;
+      // four of these run at once (side streams): pp_gemm's width choice for a GEMM alone (64 / 32 columns, to spread a long
+      // K loop over idle SMs) over-subscribes the SMs 2.6-fold; 128 / 64 keep the MMAs wide (A/B: 10 389 / 10 389 persons/s
+      // against 10 367 / 10 252 with the automatic widths)
+      if (e->fork_ev) g.tile_n = j == 1 ? 128 : 64;
       PP_TRY(gemm(e, g, bs));
       if (bs != st) {
         PP_CHECK_CUDA(cudaEventRecord(e->join_ev[br - 1], bs));
