@@ -462,8 +462,13 @@ static int run_head(pp_engine* e, int n_img, float* logits, float* scalars, cuda
       g.ldd = 4 * D; g.d = e->at<float>(e->c_f32) + br * D;
       // four of these run at once (side streams): pp_gemm's width choice for a GEMM alone (64 / 32 columns, to spread a long
       // K loop over idle SMs) over-subscribes the SMs 2.6-fold; 128 / 64 keep the MMAs wide (A/B: 10 389 / 10 389 persons/s
-      // against 10 367 / 10 252 with the automatic widths)
-      if (e->fork_ev) g.tile_n = j == 1 ? 128 : 64;
+      // against 10 367 / 10 252 with the automatic widths at 64 crops with the flipped pass)
+      if (e->fork_ev) {  // the widest tile that still gives the four GEMMs together half an SM count of tiles
+        const int64_t mt = (rows + 127) / 128;
+        g.tile_n = 32;
+        for (int bn = 128; bn > 32; bn >>= 1)
+          if (4 * mt * ((D + bn - 1) / bn) >= device_sm_count() / 2) { g.tile_n = bn; break; }
+      }
       PP_TRY(gemm(e, g, bs));
       if (bs != st) {
         PP_CHECK_CUDA(cudaEventRecord(e->join_ev[br - 1], bs));
